@@ -1,0 +1,73 @@
+"""ctypes binding of libflowmc_b200.so (the C ABI declared in include/flowmc_b200.h).
+
+There is deliberately no fallback: if the shared object is missing or a call fails, an
+exception is raised.  Nothing here imports the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libflowmc_b200.so"
+
+
+class FlowmcError(RuntimeError):
+    pass
+
+
+class LocalParams(C.Structure):
+    _fields_ = [
+        ("step_size", C.c_float),
+        ("n_leapfrog", C.c_int),
+        ("hmc_chol", C.c_void_p),
+        ("hmc_colsum", C.c_void_p),
+        ("hmc_chol_diagonal", C.c_int),
+        ("layout_hint", C.c_int),
+        ("step_keys", C.c_void_p),
+        ("lp0", C.c_void_p),
+    ]
+
+
+def _load() -> C.CDLL:
+    if not _LIB_PATH.exists():
+        raise ImportError(
+            f"{_LIB_PATH} not found: the CUDA library has not been built. "
+            "Run `python -m flowmc_b200.build` (needs nvcc); there is no CPU fallback."
+        )
+    lib = C.CDLL(str(_LIB_PATH), mode=C.RTLD_GLOBAL)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    u32p = C.POINTER(C.c_uint32)
+    sigs = {
+        "flowmc_abi_version": (i32, []),
+        "flowmc_last_error": (C.c_char_p, []),
+        "flowmc_target_count": (i32, []),
+        "flowmc_target_lookup": (i32, [C.c_char_p]),
+        "flowmc_target_name": (C.c_char_p, [i32]),
+        "flowmc_target_eval": (i32, [i32, vp, vp, i64, i32, vp, vp, vp]),
+        "flowmc_key_split": (i32, [u32p, i64, u32p]),
+        "flowmc_random_bits": (i32, [u32p, i64, vp, vp]),
+        "flowmc_random_uniform": (i32, [u32p, i64, f32, f32, vp, vp]),
+        "flowmc_random_normal": (i32, [u32p, i64, vp, vp]),
+        "flowmc_local_steps": (i32, [i32, i32, vp, u32p, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i64, i64,
+                                     C.POINTER(LocalParams), u32p, vp, vp]),
+        "flowmc_launch_count": (i64, []),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        raise FlowmcError(f"flowmc_b200 error {rc}: {lib.flowmc_last_error().decode()}")
+    return rc
+
+
+def load_plugin(path: str) -> None:
+    """dlopen a target plugin built against include/flowmc_target.cuh (registers itself)."""
+    C.CDLL(str(path), mode=C.RTLD_GLOBAL)

@@ -1,0 +1,513 @@
+// Persistent local-step kernels for sm_100a: MALA, HMC and Gaussian random walk.
+//
+// One launch runs ALL n_steps of TakeSerialSteps for a batch of chains:
+//   reference path  TakeSteps.__call__ -> jit(vmap(TakeSerialSteps.sample)) -> lax.scan(body)
+//                   (src/flowMC/strategy/take_steps.py:60-144,156-180) with
+//                   MALA.kernel (resource/kernel/MALA.py:26-89), HMC.kernel (HMC.py:98-151),
+//                   GaussianRandomWalk.kernel (Gaussian_random_walk.py:25-61)
+//   plus the three Buffer.update_buffer copies (resource/buffers.py:32-41), which become direct
+//   streaming stores into the chain-major sample buffers at the strategy's cursor.
+//
+// Mapping.  A chain lives in a group of G lanes of one warp; each lane owns DPL dimensions in
+// registers (position, cached gradient, proposal).  Dimension j of slot k on lane lg is
+//   j = (k / VEC) * (G * VEC) + lg * VEC + (k % VEC)
+// so that a warp-wide VEC-wide store of slot block k/VEC writes G*VEC contiguous floats per chain
+// (full 32B sectors for VEC=4).  32/G chains share a warp, one warp per CTA (no CTA-level
+// synchronisation anywhere), so the grid is ceil(n_chains / (32/G)) tiny CTAs that the block
+// scheduler spreads round-robin over the 148 SMs.
+//
+// RNG.  Per chain and step the reference consumes d+5 threefry2x32 blocks:
+//   (k_c, s) = split(k_c); (key1, key2) = split(s); z = normal(key1, (d,)); u = uniform(key2).
+// The d normals are drawn by the owning lanes (DPL independent blocks per lane -> ILP).  The
+// five key-schedule blocks are warp-uniform work, so they are batched over chunks of 32 steps:
+// the serial k_c chain runs once per chunk, then the 32 steps' (s, key1, key2, u) are computed
+// one step per lane and parked in shared memory.  Bits are identical to jax.random's.
+//
+// The gradient of the current point is carried across steps (the reference recomputes it every
+// step, MALA.py:59 -- same value, half the work).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "rng.cuh"
+#include "registry.h"
+
+namespace flowmc {
+
+enum : int { KIND_MALA = 0, KIND_HMC = 1, KIND_GRW = 2 };
+
+constexpr int kChunk = 32;  // steps per key-schedule chunk (= one step per lane)
+
+template <int G, int DPL, int VEC>
+struct Layout {
+  static constexpr int kG = G, kDPL = DPL, kVEC = VEC;
+  static constexpr int CPW = 32 / G;     // chains per warp
+  static constexpr int DS = G * DPL;     // padded dimension (smem row length)
+  __device__ __forceinline__ static int dim(int k, int lg) {
+    return (k / VEC) * (G * VEC) + lg * VEC + (k % VEC);
+  }
+};
+
+template <int CPW, int DS>
+struct WarpSmem {
+  float xrow[CPW][DS];
+  float scratch[CPW][DS];
+  uint32_t k0[CPW][kChunk];
+  uint32_t k1[CPW][kChunk];
+  float logu[CPW][kChunk];
+  float lpst[CPW][kChunk];
+  float accst[CPW][kChunk];
+};
+
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One evaluation of target T at the point held in xv (slot layout L); returns logp on every lane
+// of the group and, if WANT_GRAD, the owned gradient entries in gv.
+template <class T, class L, bool WANT_GRAD>
+__device__ __forceinline__ float eval_target(const float (&xv)[L::kDPL], float (&gv)[L::kDPL], float* xrow,
+                                             float* scratch, const float* data, int d, int lg) {
+  constexpr int DPL = L::kDPL, VEC = L::kVEC, G = L::kG;
+  // stage the point in shared memory so the target sees the whole vector
+#pragma unroll
+  for (int k = 0; k < DPL; k += VEC) {
+    const int j = L::dim(k, lg);
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(xrow + j) = make_float4(xv[k], xv[k + 1], xv[k + 2], xv[k + 3]);
+    } else if (VEC == 2) {
+      *reinterpret_cast<float2*>(xrow + j) = make_float2(xv[k], xv[k + 1]);
+    } else {
+      xrow[j] = xv[k];
+    }
+  }
+  __syncwarp();
+  TargetCtx ctx{xrow, scratch, data, d};
+  float red[T::NRED];
+#pragma unroll
+  for (int r = 0; r < T::NRED; ++r) red[r] = 0.0f;
+  float aux[DPL];
+#pragma unroll
+  for (int k = 0; k < DPL; ++k) {
+    const int j = L::dim(k, lg);
+    aux[k] = 0.0f;
+    if (j < d) aux[k] = T::partial(ctx, j, xv[k], red);
+  }
+  if (T::USES_SCRATCH) __syncwarp();
+#pragma unroll
+  for (int r = 0; r < T::NRED; ++r) red[r] = group_sum<G>(red[r]);
+  const float lp = T::finish(ctx, red);
+  if (WANT_GRAD) {
+#pragma unroll
+    for (int k = 0; k < DPL; ++k) {
+      const int j = L::dim(k, lg);
+      gv[k] = (j < d) ? T::grad(ctx, j, xv[k], aux[k], red) : 0.0f;
+    }
+  }
+  __syncwarp();  // xrow/scratch may be overwritten by the next evaluation
+  return lp;
+}
+
+template <class L>
+__device__ __forceinline__ void store_row(float* dst, const float (&xv)[L::kDPL], int d, int lg) {
+  constexpr int DPL = L::kDPL, VEC = L::kVEC;
+#pragma unroll
+  for (int k = 0; k < DPL; k += VEC) {
+    const int j = L::dim(k, lg);
+    if (j < d) {
+      if (VEC == 4) {
+        __stcs(reinterpret_cast<float4*>(dst + j), make_float4(xv[k], xv[k + 1], xv[k + 2], xv[k + 3]));
+      } else if (VEC == 2) {
+        __stcs(reinterpret_cast<float2*>(dst + j), make_float2(xv[k], xv[k + 1]));
+      } else {
+        __stcs(dst + j, xv[k]);
+      }
+    }
+  }
+}
+
+template <class T, int KIND, class L, int MINB>
+__global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a) {
+  constexpr int G = L::kG, DPL = L::kDPL, CPW = L::CPW, DS = L::DS;
+  __shared__ __align__(16) WarpSmem<CPW, DS> sm;
+
+  const int lane = threadIdx.x;
+  const int lg = lane % G;
+  const int cw = lane / G;
+  int64_t chain = (int64_t)blockIdx.x * CPW + cw;
+  const bool active = chain < a.n_chains;
+  if (!active) chain = a.n_chains - 1;  // idle groups shadow the last chain; their stores are masked
+  const int d = a.d;
+  float* xrow = sm.xrow[cw];
+  float* scratch = sm.scratch[cw];
+
+  // per-chain key: split(subkey, n_chains_global)[global chain index]   (take_steps.py:72)
+  Key kc = split_at(a.subkey, (uint64_t)(a.chain_offset + chain));
+
+  float x[DPL], g[DPL];
+#pragma unroll
+  for (int k = 0; k < DPL; ++k) {
+    const int j = L::dim(k, lg);
+    x[k] = (j < d) ? a.x0[chain * d + j] : 0.0f;
+    g[k] = 0.0f;
+  }
+  // logpdf(initial_position) seeds the scan carry (take_steps.py:177); MALA/HMC also cache the gradient
+  float lp = eval_target<T, L, KIND != KIND_GRW>(x, g, xrow, scratch, a.data, d, lg);
+  if (a.lp0 != nullptr) lp = a.lp0[chain];  // ProposalBase.kernel(): caller-supplied log_prob
+
+  const float dt = a.step_size;
+  const float dt2 = dt * dt;
+  // scalar-covariance multivariate_normal.logpdf constant: n/2 * (log(2 pi) + log(cov))
+  const float mvn_c = (float)d * 0.5f * (1.8378770664093453f + logf(dt2));
+
+  float cs[DPL], ld[DPL];  // HMC: column sums of the metric, diagonal of L
+#pragma unroll
+  for (int k = 0; k < DPL; ++k) {
+    cs[k] = 0.0f;
+    ld[k] = 0.0f;
+    if (KIND == KIND_HMC) {
+      const int j = L::dim(k, lg);
+      if (j < d) {
+        cs[k] = a.hmc_colsum[j];
+        ld[k] = a.hmc_chol[(int64_t)j * d + j];
+      }
+    }
+  }
+
+  const int thin = a.thinning;
+  const int t_last_stored = ((a.n_steps - 1) / thin) * thin;
+
+  for (int t0 = 0; t0 < a.n_steps; t0 += kChunk) {
+    const int nb = min(kChunk, a.n_steps - t0);
+    // ---- key schedule for this chunk -------------------------------------------------
+    // serial part: k_c^{t+1} = split(k_c^t)[0]   (take_steps.py:158)
+    for (int t = 0; t < nb; ++t) {
+      if (lg == 0) {
+        sm.k0[cw][t] = kc.k0;
+        sm.k1[cw][t] = kc.k1;
+      }
+      kc = split_at(kc, 0);
+    }
+    __syncwarp();
+    // parallel part, one step per lane: s = split(k_c^t)[1]; key1, key2 = split(s)  (MALA.py:66);
+    // log(uniform(key2))  (MALA.py:83)
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) {
+      Key kt{sm.k0[c][lane], sm.k1[c][lane]};
+      Key s = split_at(kt, 1);
+      if (a.step_keys != nullptr) {  // single kernel() call with explicit per-chain keys
+        const int64_t ch = min((int64_t)blockIdx.x * CPW + c, a.n_chains - 1);
+        s = Key{a.step_keys[2 * ch], a.step_keys[2 * ch + 1]};
+      }
+      Key key1 = split_at(s, 0);
+      Key key2 = split_at(s, 1);
+      const float u = bits_to_uniform01(bits_at(key2, 0));
+      sm.k0[c][lane] = key1.k0;
+      sm.k1[c][lane] = key1.k1;
+      sm.logu[c][lane] = logf(u);
+    }
+    __syncwarp();
+
+    const int o_first = (t0 + thin - 1) / thin;  // first output index of this chunk
+    // ---- steps ---------------------------------------------------------------------------
+    for (int tt = 0; tt < nb; ++tt) {
+      const int t = t0 + tt;
+      const Key key1{sm.k0[cw][tt], sm.k1[cw][tt]};
+      const float logu = sm.logu[cw][tt];
+      bool acc;
+
+      if (KIND == KIND_MALA) {
+        float prop[DPL], g1[DPL];
+        float qa = 0.0f;
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) {
+          const int j = L::dim(k, lg);
+          prop[k] = 0.0f;
+          if (j < d) {
+            const float z = bits_to_normal(bits_at(key1, (uint64_t)j));
+            const float mean = x[k] + (dt2 * g[k]) / 2.0f;  // MALA.py:60
+            prop[k] = mean + dt * z;                        // MALA.py:61-63
+            const float y = prop[k] - mean;
+            qa += y * y;
+          }
+        }
+        const float lp1 = eval_target<T, L, true>(prop, g1, xrow, scratch, a.data, d, lg);
+        float qb = 0.0f;
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) {
+          const float y = x[k] - (prop[k] + (dt2 * g1[k]) / 2.0f);
+          qb += y * y;
+        }
+        qa = group_sum<G>(qa);
+        qb = group_sum<G>(qb);
+        // MALA.py:75-81
+        float ratio = lp1 - lp;
+        ratio -= (-0.5f * qa / dt2 - mvn_c);
+        ratio += (-0.5f * qb / dt2 - mvn_c);
+        acc = logu < ratio;
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) {
+          x[k] = acc ? prop[k] : x[k];
+          g[k] = acc ? g1[k] : g[k];
+        }
+        lp = acc ? lp1 : lp;
+      } else if (KIND == KIND_GRW) {
+        float prop[DPL], g1[DPL];
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) {
+          const int j = L::dim(k, lg);
+          prop[k] = 0.0f;
+          if (j < d) {
+            const float z = bits_to_normal(bits_at(key1, (uint64_t)j));
+            prop[k] = x[k] + z * dt;  // Gaussian_random_walk.py:49-52
+          }
+        }
+        const float lp1 = eval_target<T, L, false>(prop, g1, xrow, scratch, a.data, d, lg);
+        acc = logu < (lp1 - lp);  // Gaussian_random_walk.py:56
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) x[k] = acc ? prop[k] : x[k];
+        lp = acc ? lp1 : lp;
+      } else {  // HMC
+        float xs[DPL], p[DPL], g1[DPL];
+        // momentum = normal(key1) @ chol(inv(M)).T   (HMC.py:133-136)
+        if (a.hmc_diag) {
+#pragma unroll
+          for (int k = 0; k < DPL; ++k) {
+            const int j = L::dim(k, lg);
+            p[k] = 0.0f;
+            if (j < d) p[k] = bits_to_normal(bits_at(key1, (uint64_t)j)) * ld[k];
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < DPL; ++k) {
+            const int j = L::dim(k, lg);
+            if (j < d) scratch[j] = bits_to_normal(bits_at(key1, (uint64_t)j));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < DPL; ++k) {
+            const int j = L::dim(k, lg);
+            float s = 0.0f;
+            if (j < d) {
+              const float* Lrow = a.hmc_chol + (int64_t)j * d;
+              for (int i = 0; i <= j; ++i) s = fmaf(scratch[i], Lrow[i], s);
+            }
+            p[k] = s;
+          }
+          __syncwarp();
+        }
+        float kin = 0.0f;
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) kin += p[k] * p[k] * cs[k];
+        kin = 0.5f * group_sum<G>(kin);
+        const float H = -lp + kin;  // HMC.py:137
+        // leapfrog_step (HMC.py:82-96): rows [0,.5], n_leapfrog x [1,1], [1,.5].
+        // Row 0 moves the position by eps*0*dK/dp = 0 and uses the gradient at the current point,
+        // which is the cached g.
+        const float eps = a.step_size;
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) {
+          xs[k] = x[k];
+          p[k] = p[k] - (eps * 0.5f) * (-g[k]);
+        }
+        float lp1 = lp;
+        for (int it = 1; it <= a.n_leapfrog + 1; ++it) {
+          const float c1 = (it == a.n_leapfrog + 1) ? 0.5f : 1.0f;
+#pragma unroll
+          for (int k = 0; k < DPL; ++k) xs[k] = xs[k] + (eps * 1.0f) * (p[k] * cs[k]);
+          lp1 = eval_target<T, L, true>(xs, g1, xrow, scratch, a.data, d, lg);
+#pragma unroll
+          for (int k = 0; k < DPL; ++k) p[k] = p[k] - (eps * c1) * (-g1[k]);
+        }
+        float kin1 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) kin1 += p[k] * p[k] * cs[k];
+        kin1 = 0.5f * group_sum<G>(kin1);
+        const float ham = -lp1 + kin1;  // HMC.py:141-142
+        acc = logu < (H - ham);         // HMC.py:143-146
+#pragma unroll
+        for (int k = 0; k < DPL; ++k) {
+          x[k] = acc ? xs[k] : x[k];
+          g[k] = acc ? g1[k] : g[k];
+        }
+        lp = acc ? lp1 : lp;
+      }
+
+      // ---- outputs (take_steps.py:134-142): thinned, written in place at the cursor ----------
+      if (t % thin == 0) {
+        const int64_t o = t / thin;
+        if (active) store_row<L>(a.pos_buf + (chain * a.n_total + a.cursor + o) * d, x, d, lg);
+        if (lg == 0) {
+          sm.lpst[cw][o - o_first] = lp;
+          sm.accst[cw][o - o_first] = acc ? 1.0f : 0.0f;
+        }
+        if (t == t_last_stored && active) store_row<L>(a.last_pos + chain * d, x, d, lg);
+      }
+    }
+    __syncwarp();
+    // flush this chunk's log-probs and accept flags: one coalesced row per chain
+    const int o_end = (t0 + nb + thin - 1) / thin;  // one past the last output index of the chunk
+    const int n_out = o_end - o_first;
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) {
+      const int64_t ch = (int64_t)blockIdx.x * CPW + c;
+      if (ch < a.n_chains && lane < n_out) {
+        const int64_t off = ch * a.n_total + a.cursor + o_first + lane;
+        __stcs(a.lp_buf + off, sm.lpst[c][lane]);
+        __stcs(a.acc_buf + off, sm.accst[c][lane]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- target evaluation kernel (LogPDF.__call__ / value_and_grad) -----------------------------
+template <class T, class L>
+__global__ void __launch_bounds__(32) target_eval_kernel(const float* __restrict__ data, const float* __restrict__ xin,
+                                                         int64_t n, int d, float* __restrict__ lp_out,
+                                                         float* __restrict__ grad_out) {
+  constexpr int G = L::kG, DPL = L::kDPL, CPW = L::CPW, DS = L::DS;
+  __shared__ __align__(16) float xrow[CPW][DS];
+  __shared__ __align__(16) float scratch[CPW][DS];
+  const int lane = threadIdx.x, lg = lane % G, cw = lane / G;
+  int64_t i = (int64_t)blockIdx.x * CPW + cw;
+  const bool active = i < n;
+  if (!active) i = n - 1;
+  float x[DPL], g[DPL];
+#pragma unroll
+  for (int k = 0; k < DPL; ++k) {
+    const int j = L::dim(k, lg);
+    x[k] = (j < d) ? xin[i * d + j] : 0.0f;
+    g[k] = 0.0f;
+  }
+  float lp;
+  if (grad_out != nullptr) {
+    lp = eval_target<T, L, true>(x, g, xrow[cw], scratch[cw], data, d, lg);
+  } else {
+    lp = eval_target<T, L, false>(x, g, xrow[cw], scratch[cw], data, d, lg);
+  }
+  if (active) {
+    if (lg == 0) lp_out[i] = lp;
+    if (grad_out != nullptr) {
+#pragma unroll
+      for (int k = 0; k < DPL; ++k) {
+        const int j = L::dim(k, lg);
+        if (j < d) grad_out[i * d + j] = g[k];
+      }
+    }
+  }
+}
+
+// ---- layout table and launchers --------------------------------------------------------------
+// index: 0:(1,8,1) 1:(4,8,1) 2:(8,8,1) 3:(32,16,1) | 4:(8,4,4) 5:(8,8,4) 6:(16,4,4) 7:(8,16,4)
+//        8:(16,8,4) 9:(32,4,4) 10:(16,16,4) 11:(32,8,4) 12:(32,16,4)
+constexpr int kNumLayouts = 13;
+
+struct LayoutInfo {
+  int G, DPL, VEC;
+};
+__host__ inline LayoutInfo layout_info(int idx) {
+  static const LayoutInfo tab[kNumLayouts] = {{1, 8, 1},  {4, 8, 1},  {8, 8, 1},   {32, 16, 1}, {8, 4, 4},
+                                              {8, 8, 4},  {16, 4, 4}, {8, 16, 4},  {16, 8, 4},  {32, 4, 4},
+                                              {16, 16, 4}, {32, 8, 4}, {32, 16, 4}};
+  return tab[idx];
+}
+
+__host__ inline int pick_layout(int d, int hint) {
+  if (hint > 0 && hint <= kNumLayouts) {
+    const LayoutInfo li = layout_info(hint - 1);
+    if (li.G * li.DPL >= d && (li.VEC == 1 || d % li.VEC == 0)) return hint - 1;
+  }
+  if (d % 4 == 0) {
+    if (d <= 32) return 4;
+    if (d <= 64) return 5;
+    if (d <= 128) return 7;
+    if (d <= 256) return 10;
+    if (d <= 512) return 12;
+    return -1;
+  }
+  if (d <= 8) return 0;
+  if (d <= 32) return 1;
+  if (d <= 64) return 2;
+  if (d <= 512) return 3;
+  return -1;
+}
+
+template <class T, int KIND, int G, int DPL, int VEC, int MINB>
+inline int launch_local_one(const LocalArgs* a, cudaStream_t stream) {
+  using L = Layout<G, DPL, VEC>;
+  const int64_t nblk = (a->n_chains + L::CPW - 1) / L::CPW;
+  local_steps_kernel<T, KIND, L, MINB><<<(unsigned)nblk, 32, 0, stream>>>(*a);
+  flowmc_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    flowmc_set_error(cudaGetErrorString(e));
+    return -3;
+  }
+  return 0;
+}
+
+template <class T, int KIND>
+inline int launch_local_kind(const LocalArgs* a, cudaStream_t stream) {
+  const int li = pick_layout(a->d, a->layout_hint);
+  switch (li) {
+    case 0: return launch_local_one<T, KIND, 1, 8, 1, 16>(a, stream);
+    case 1: return launch_local_one<T, KIND, 4, 8, 1, 16>(a, stream);
+    case 2: return launch_local_one<T, KIND, 8, 8, 1, 16>(a, stream);
+    case 3: return launch_local_one<T, KIND, 32, 16, 1, 12>(a, stream);
+    case 4: return launch_local_one<T, KIND, 8, 4, 4, 24>(a, stream);
+    case 5: return launch_local_one<T, KIND, 8, 8, 4, 16>(a, stream);
+    case 6: return launch_local_one<T, KIND, 16, 4, 4, 24>(a, stream);
+    case 7: return launch_local_one<T, KIND, 8, 16, 4, 12>(a, stream);
+    case 8: return launch_local_one<T, KIND, 16, 8, 4, 16>(a, stream);
+    case 9: return launch_local_one<T, KIND, 32, 4, 4, 24>(a, stream);
+    case 10: return launch_local_one<T, KIND, 16, 16, 4, 12>(a, stream);
+    case 11: return launch_local_one<T, KIND, 32, 8, 4, 16>(a, stream);
+    case 12: return launch_local_one<T, KIND, 32, 16, 4, 12>(a, stream);
+    default:
+      flowmc_set_error("local_steps: unsupported dimension (d must be <= 512)");
+      return -2;
+  }
+}
+
+template <class T>
+int launch_local_steps(int kind, const LocalArgs* a, cudaStream_t stream) {
+  switch (kind) {
+    case KIND_MALA: return launch_local_kind<T, KIND_MALA>(a, stream);
+    case KIND_HMC: return launch_local_kind<T, KIND_HMC>(a, stream);
+    case KIND_GRW: return launch_local_kind<T, KIND_GRW>(a, stream);
+    default:
+      flowmc_set_error("local_steps: unknown kernel kind");
+      return -1;
+  }
+}
+
+template <class T, int G, int DPL, int VEC>
+inline int launch_eval_one(const float* data, const float* x, int64_t n, int d, float* lp, float* grad,
+                           cudaStream_t stream) {
+  using L = Layout<G, DPL, VEC>;
+  const int64_t nblk = (n + L::CPW - 1) / L::CPW;
+  target_eval_kernel<T, L><<<(unsigned)nblk, 32, 0, stream>>>(data, x, n, d, lp, grad);
+  flowmc_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    flowmc_set_error(cudaGetErrorString(e));
+    return -3;
+  }
+  return 0;
+}
+
+template <class T>
+int launch_target_eval(const float* data, const float* x, int64_t n, int d, float* lp, float* grad,
+                       cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (d <= 8) return launch_eval_one<T, 1, 8, 1>(data, x, n, d, lp, grad, stream);
+  if (d <= 64) return launch_eval_one<T, 8, 8, 1>(data, x, n, d, lp, grad, stream);
+  if (d <= 512) return launch_eval_one<T, 32, 16, 1>(data, x, n, d, lp, grad, stream);
+  flowmc_set_error("target_eval: unsupported dimension (d must be <= 512)");
+  return -2;
+}
+
+}  // namespace flowmc

@@ -1,0 +1,52 @@
+// Internal ABI between target plugins (instantiated kernel launchers) and the core library.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "rng.cuh"
+
+#define FLOWMC_TARGET_ABI 1
+
+namespace flowmc {
+
+// Arguments of one persistent local-steps launch (POD, passed by value to the kernel).
+struct LocalArgs {
+  const float* data;      // packed target parameters (device)
+  const float* x0;        // [n_chains, d]
+  float* pos_buf;         // [n_chains, n_total, d]
+  float* lp_buf;          // [n_chains, n_total]
+  float* acc_buf;         // [n_chains, n_total]
+  float* last_pos;        // [n_chains, d]
+  int64_t n_total;
+  int64_t cursor;
+  int64_t n_chains;
+  int64_t chain_offset;   // global index of local chain 0
+  int d;
+  int n_steps;
+  int thinning;
+  Key subkey;             // chain c uses split(subkey, n_chains_global)[chain_offset + c]
+  float step_size;
+  int n_leapfrog;
+  const float* hmc_chol;  // [d,d] lower-triangular L
+  const float* hmc_colsum;// [d]
+  int hmc_diag;
+  int layout_hint;
+  const uint32_t* step_keys;  // optional [n_chains,2]; n_steps must be 1
+  const float* lp0;           // optional [n_chains]
+};
+
+}  // namespace flowmc
+
+extern "C" {
+typedef struct FlowmcTargetVTable {
+  int abi_version;
+  const char* name;
+  // returns 0, or a negative FLOWMC_ERR_* code (message via flowmc_set_error)
+  int (*local_steps)(int kind, const flowmc::LocalArgs* args, cudaStream_t stream);
+  int (*eval)(const float* data, const float* x, int64_t n, int d, float* logp_out, float* grad_out,
+              cudaStream_t stream);
+} FlowmcTargetVTable;
+
+__attribute__((visibility("default"))) int flowmc_register_target(const FlowmcTargetVTable* vt);
+__attribute__((visibility("default"))) void flowmc_set_error(const char* msg);
+__attribute__((visibility("default"))) void flowmc_count_launch(void);
+}

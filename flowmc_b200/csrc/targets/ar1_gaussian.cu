@@ -1,0 +1,24 @@
+// ar1_gaussian (BASELINE.json configs[1]): zero-mean Gaussian with covariance
+// rho^|i-j|, i.e. tridiagonal precision P = 1/(1-rho^2) * tridiag(-rho, 1+rho^2 (1 at the ends), -rho).
+// logp = -1/2 x^T P x,  grad = -P x.   data = [rho].
+#include "../../../include/flowmc_target.cuh"
+
+struct AR1Gaussian {
+  static constexpr int NRED = 1;
+  static constexpr bool USES_SCRATCH = false;
+  __device__ static float partial(const flowmc::TargetCtx& c, int j, float xj, float* red) {
+    const float rho = c.data[0];
+    const float a = 1.0f / (1.0f - rho * rho);
+    const float left = (j > 0) ? c.x[j - 1] : 0.0f;
+    const float right = (j < c.d - 1) ? c.x[j + 1] : 0.0f;
+    const float diag = (j > 0 && j < c.d - 1) ? 1.0f + rho * rho : 1.0f;
+    const float px = a * (diag * xj - rho * (left + right));
+    red[0] += xj * px;
+    return px;
+  }
+  __device__ static float finish(const flowmc::TargetCtx& c, float* red) { return -0.5f * red[0]; }
+  __device__ static float grad(const flowmc::TargetCtx& c, int j, float xj, float aux, const float* red) {
+    return -aux;
+  }
+};
+FLOWMC_REGISTER_TARGET(AR1Gaussian, "ar1_gaussian")

@@ -1,0 +1,28 @@
+// rosenbrock (BASELINE.json configs[2]):
+//   logp = -sum_{i<d-1} [100 (x_{i+1} - x_i^2)^2 + (1 - x_i)^2] / 20.   No data.
+#include "../../../include/flowmc_target.cuh"
+
+struct Rosenbrock {
+  static constexpr int NRED = 1;
+  static constexpr bool USES_SCRATCH = false;
+  __device__ static float partial(const flowmc::TargetCtx& c, int j, float xj, float* red) {
+    float gj = 0.0f;
+    if (j < c.d - 1) {
+      const float u = c.x[j + 1] - xj * xj;
+      const float v = 1.0f - xj;
+      red[0] += (100.0f * u * u + v * v) / 20.0f;
+      gj += (400.0f * xj * u + 2.0f * v) / 20.0f;
+    }
+    if (j > 0) {
+      const float xm = c.x[j - 1];
+      const float um = xj - xm * xm;
+      gj += (-200.0f * um) / 20.0f;
+    }
+    return gj;
+  }
+  __device__ static float finish(const flowmc::TargetCtx& c, float* red) { return -red[0]; }
+  __device__ static float grad(const flowmc::TargetCtx& c, int j, float xj, float aux, const float* red) {
+    return aux;
+  }
+};
+FLOWMC_REGISTER_TARGET(Rosenbrock, "rosenbrock")

@@ -1,0 +1,60 @@
+// flowmc_target.cuh -- plugin header: how a target log-density reaches the B200 kernels.
+//
+// The reference hands an arbitrary Python callable to jax.value_and_grad
+// (src/flowMC/resource/logPDF.py:60-61, resource/kernel/MALA.py:59, HMC.py:76-79).  Here a
+// target is a struct of __device__ functions carrying its *analytic* gradient; the sampling
+// kernels (flowmc_b200/csrc/local_steps.cuh, nf kernels) are templates instantiated per target,
+// and FLOWMC_REGISTER_TARGET puts the instantiations into the library's registry under a name
+// that Python's LogPDF refers to.  A plugin is a .cu file that includes this header, defines a
+// struct and registers it; compile it into libflowmc_b200.so or into its own shared object
+// loaded after the library (flowmc_b200.targets.compile_target()).
+//
+// Execution model.  A chain's position x[0..d) is spread over a group of G lanes of one warp
+// (each lane owns a few dimensions, held in registers) and mirrored in a shared-memory row that
+// the target may read freely.  One evaluation is three calls:
+//
+//   aux_j = T::partial(ctx, j, x_j, red)   for every owned dimension j: add this dimension's
+//                                          contribution(s) to red[0..NRED); return any per-
+//                                          dimension value grad() will want (e.g. (P x)_j)
+//   -- the kernel sums red[] over the chain's lanes --
+//   logp  = T::finish(ctx, red)            every lane of the group: turn the reduced scalars into
+//                                          log p(x); may overwrite red[] with whatever grad() needs
+//   g_j   = T::grad(ctx, j, x_j, aux_j, red)  for every owned dimension j: d log p / d x_j
+//
+// `ctx.x` is the full vector (read-only), `ctx.data` the packed float32 parameter block built on
+// the host (the reference's `data` pytree; layout is target-defined), `ctx.scratch` a private
+// row of >= d floats in shared memory (valid only if USES_SCRATCH).  partial() of all owned
+// dimensions completes (with a warp barrier) before finish()/grad() run.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace flowmc {
+
+struct TargetCtx {
+  const float* x;      // shared memory: x[0..d)
+  float* scratch;      // shared memory: >= d floats, private to this chain (if USES_SCRATCH)
+  const float* data;   // global memory: packed target parameters
+  int d;
+};
+
+}  // namespace flowmc
+
+#include "../flowmc_b200/csrc/local_steps.cuh"
+#include "../flowmc_b200/csrc/registry.h"
+
+// Registers target struct T under `NAME` at load time (static initialiser).
+#define FLOWMC_REGISTER_TARGET(T, NAME)                                                         \
+  namespace {                                                                                   \
+  struct FlowmcRegistrar_##T {                                                                  \
+    FlowmcRegistrar_##T() {                                                                     \
+      static FlowmcTargetVTable vt;                                                             \
+      vt.abi_version = FLOWMC_TARGET_ABI;                                                       \
+      vt.name = NAME;                                                                           \
+      vt.local_steps = &flowmc::launch_local_steps<T>;                                          \
+      vt.eval = &flowmc::launch_target_eval<T>;                                                 \
+      flowmc_register_target(&vt);                                                              \
+    }                                                                                           \
+  };                                                                                            \
+  static FlowmcRegistrar_##T flowmc_registrar_instance_##T;                                     \
+  }

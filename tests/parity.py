@@ -1,0 +1,54 @@
+"""Shared parity helpers: compare a CUDA run with the oracle on the same seeds.
+
+Tolerances (BASELINE.json north_star): RNG words and accept/reject decisions bit-exact;
+positions and log-probs within 1e-5 relative in fp32.  Accept decisions compare two fp32
+numbers (``log_u < ratio``); under any reassociation of the fp32 sums a decision can only differ
+where the two are within rounding of each other, so a chain whose flags differ from the oracle's
+must have its FIRST difference at such a near-tie -- everything before it must still match -- and
+the number of such chains is asserted to be tiny.
+"""
+import numpy as np
+
+RTOL = 1e-5
+
+
+def assert_close(a, b, what, rtol=RTOL, scale=None):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin), f"{what}: finite masks differ"
+    if scale is None:
+        scale = max(1.0, float(np.max(np.abs(b[fin]))) if fin.any() else 1.0)
+    err = np.abs(a[fin] - b[fin])
+    tol = rtol * np.maximum(np.abs(b[fin]), scale)
+    bad = err > tol
+    assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} beyond rtol={rtol}; max err {err.max():.3e} (scale {scale:.3g})"
+
+
+def compare_chains(gpu, ora, dbg, max_diverged_frac=0.01, rtol=RTOL, tie_tol=1e-4):
+    """gpu/ora = (positions[n,T,d], log_probs[n,T], accepts[n,T]); dbg = per-step oracle info
+    (ratio, log_u).  Returns the number of chains that diverged at a near-tie."""
+    gp, gl, ga = [np.asarray(v) for v in gpu]
+    op, ol, oa = [np.asarray(v) for v in ora]
+    n, T = oa.shape
+    diverged = 0
+    scale_p = max(1.0, float(np.abs(op).max()))
+    scale_l = max(1.0, float(np.abs(ol[np.isfinite(ol)]).max()))
+    for c in range(n):
+        diff = np.nonzero(ga[c] != oa[c])[0]
+        upto = T
+        if diff.size:
+            t = int(diff[0])
+            margin = abs(float(dbg[t]["ratio"][c]) - float(dbg[t]["log_u"][c]))
+            mag = max(1.0, abs(float(dbg[t]["ratio"][c])))
+            assert margin <= tie_tol * mag, (
+                f"chain {c}: accept flag differs at step {t} but it is not a near-tie "
+                f"(ratio={dbg[t]['ratio'][c]}, log_u={dbg[t]['log_u'][c]})")
+            diverged += 1
+            upto = t
+        if upto:
+            assert_close(gp[c, :upto], op[c, :upto], f"chain {c} positions", rtol, scale_p)
+            assert_close(gl[c, :upto], ol[c, :upto], f"chain {c} log_probs", rtol, scale_l)
+    assert diverged <= max(1, int(max_diverged_frac * n)), f"{diverged} of {n} chains diverged"
+    return diverged
