@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the flowMC sampling hot path on B200.
+
+Workload (BASELINE.json configs[1], the config the chain-steps/s metric is quoted on and the
+largest local-step config that is defined for one GPU): 128-D AR(1)-correlated Gaussian,
+8192 chains per GPU, MALA step_size=0.1, one "step" = one TakeSerialSteps call of 1000 MALA
+steps for every chain (8.192 M chain-steps, 4.26 GB of samples written, >> the 126 MB L2, so no
+L2 flush is needed between steps).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU); chains shard across ranks with no
+communication on the data path (weak scaling: 8192 chains per GPU, global chain index keys).
+Rank 0 prints ONE JSON line.  `--impl reference` times the CPU stand-in for the reference (the C
+restatement under oracle/, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D = 128
+CHAINS_PER_GPU = 8192
+N_LOCAL_STEPS = 1000
+STEP_SIZE = 0.1
+RHO = 0.9
+BYTES_PER_CHAIN_STEP = 4 * (D + 2)  # position (d fp32) + log-prob + accept flag, SURVEY.md 8(d)
+WORKLOAD = "C2: 128-D AR(1) Gaussian (rho=0.9), 8192 chains/GPU, MALA step_size=0.1, 1000 local steps per call"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        busy = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)]
+        return {"sm_mhz": float(np.median(busy or sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(target_seconds: float = 12.0):
+    """C restatement (oracle/c, OpenMP over chains) on a bounded sample of the workload."""
+    from oracle import cref, rng, targets as otargets
+    key = rng.PRNGKey(1)
+    n = CHAINS_PER_GPU
+    x0 = rng.normal(rng.split(rng.PRNGKey(0))[1], (n, D))
+    data = otargets.AR1Gaussian.pack(D, RHO)
+    cref.take_serial_steps(key, x0, "ar1_gaussian", data, "MALA", 1, step_size=STEP_SIZE, store=False)  # warm
+    t0 = time.perf_counter()
+    cref.take_serial_steps(key, x0, "ar1_gaussian", data, "MALA", 2, step_size=STEP_SIZE, store=False)
+    per_step = (time.perf_counter() - t0) / 2
+    steps = int(max(2, min(N_LOCAL_STEPS, target_seconds / max(per_step, 1e-6))))
+    t0 = time.perf_counter()
+    cref.take_serial_steps(key, x0, "ar1_gaussian", data, "MALA", steps, step_size=STEP_SIZE, store=True)
+    dt = time.perf_counter() - t0
+    return n * steps / dt, cref.num_threads(), steps, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cref, rng, targets as otargets
+    key = rng.PRNGKey(1)
+    n = CHAINS_PER_GPU
+    x0 = rng.normal(rng.split(rng.PRNGKey(0))[1], (n, D))
+    data = otargets.AR1Gaussian.pack(D, RHO)
+    cref.take_serial_steps(key, x0, "ar1_gaussian", data, "MALA", 1, step_size=STEP_SIZE, store=False)
+    t0 = time.perf_counter()
+    cref.take_serial_steps(key, x0, "ar1_gaussian", data, "MALA", 2, step_size=STEP_SIZE, store=False)
+    per = (time.perf_counter() - t0) / 2
+    total_budget = 120.0  # seconds for the whole --steps/--warmup run
+    sub_steps = int(max(1, min(N_LOCAL_STEPS, total_budget / max(1, args.steps + args.warmup) / max(per, 1e-6))))
+    for _ in range(args.warmup):
+        cref.take_serial_steps(key, x0, "ar1_gaussian", data, "MALA", sub_steps, step_size=STEP_SIZE)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cref.take_serial_steps(key, x0, "ar1_gaussian", data, "MALA", sub_steps, step_size=STEP_SIZE)
+    dt = time.perf_counter() - t0
+    rate = n * sub_steps * args.steps / dt
+    sample = f"{n} chains x {sub_steps} MALA steps per bench step (of {N_LOCAL_STEPS}), samples stored to host memory"
+    line = {
+        "impl": "reference", "metric": "chain-steps/s (MALA)", "value": rate, "unit": "chain-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_dim": D, "n_chains": n, "local_steps_per_bench_step": sub_steps},
+        "cpu_baseline": {"value": rate, "unit": "chain-steps/s", "cores": cref.num_threads(), "kind": "port",
+                         "sample": sample,
+                         "note": "C restatement of flowMC's MALA path (oracle/c, OpenMP over chains); the "
+                                 "reference's own JAX CPU path cannot run here (jax not installable)"},
+        "e2e": {"value": rate, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from flowmc_b200 import random as frandom, targets as T
+    from flowmc_b200._lib import lib
+    from flowmc_b200.resource.buffers import Buffer
+    from flowmc_b200.resource.kernel.MALA import MALA
+    from flowmc_b200.resource.logPDF import LogPDF
+    from flowmc_b200.resource.states import State
+    from flowmc_b200.strategy.take_steps import TakeSerialSteps
+
+    n = CHAINS_PER_GPU
+    n_global = n * world
+    resources = {
+        "positions": Buffer("positions", (n, N_LOCAL_STEPS, D), 1, device=dev),
+        "log_prob": Buffer("log_prob", (n, N_LOCAL_STEPS), 1, device=dev),
+        "acceptance": Buffer("acceptance", (n, N_LOCAL_STEPS), 1, device=dev),
+        "state": State({"p": "positions", "l": "log_prob", "a": "acceptance"}, name="state"),
+        "kernel": MALA(step_size=STEP_SIZE),
+        "logpdf": LogPDF(T.ar1_gaussian(RHO), n_dims=D),
+    }
+    strat = TakeSerialSteps("logpdf", "kernel", "state", ["p", "l", "a"], N_LOCAL_STEPS)
+    strat.set_chain_shard(rank * n, n_global)
+    # initial positions: normal(split(PRNGKey(0))[1], (n_global, d)) -- this rank's rows
+    x0_all_key = frandom.split(frandom.PRNGKey(0))[1]
+    x0 = frandom.normal(x0_all_key, (n_global, D), device=dev)[rank * n:(rank + 1) * n].contiguous()
+    x0_host = x0.cpu().pin_memory()
+    key = frandom.PRNGKey(1)
+
+    def step_device(k):
+        strat.set_current_position(0)
+        k, _, last = strat(k, resources, x0, None)
+        return k, last
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) -----------------------------------------------
+    k = key
+    for _ in range(args.warmup):
+        k, _ = step_device(k)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = lib.flowmc_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        k, last = step_device(k)
+        ev[i + 1].record()
+    barrier()
+    launches = lib.flowmc_launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    clocks = sampler.stop() if rank == 0 else None
+    acc_rate = float(resources["acceptance"].data.mean())
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    chain_steps_per_step = n_global * N_LOCAL_STEPS
+    value = chain_steps_per_step * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end-to-end through the strategy API with host buffers (`e2e`) ------------------------
+    out_pos = torch.empty((n, N_LOCAL_STEPS, D), dtype=torch.float32).pin_memory()
+    out_lp = torch.empty((n, N_LOCAL_STEPS), dtype=torch.float32).pin_memory()
+    out_acc = torch.empty((n, N_LOCAL_STEPS), dtype=torch.float32).pin_memory()
+    out_last = torch.empty((n, D), dtype=torch.float32).pin_memory()
+
+    def step_e2e(k, full):
+        strat.set_current_position(0)
+        xin = x0_host.to(dev, non_blocking=True)                 # H2D of this step's input
+        k, _, last = strat(k, resources, xin, None)
+        out_last.copy_(last, non_blocking=True)                   # D2H of the strategy's return value
+        if full:                                                  # D2H of the three sample buffers
+            out_pos.copy_(resources["positions"].data, non_blocking=True)
+            out_lp.copy_(resources["log_prob"].data, non_blocking=True)
+            out_acc.copy_(resources["acceptance"].data, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return k
+
+    e2e_steps = max(1, min(args.steps, 5))
+    res_e2e = {}
+    for full in (True, False):
+        kk = key
+        kk = step_e2e(kk, full)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            kk = step_e2e(kk, full)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        res_e2e[full] = chain_steps_per_step * e2e_steps / float(dt.item())
+    h2d = x0_host.numel() * 4
+    d2h_full = (out_pos.numel() + out_lp.numel() + out_acc.numel() + out_last.numel()) * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    avg_kernel_ms = float(np.mean(kernel_ms))
+    achieved = n * N_LOCAL_STEPS * BYTES_PER_CHAIN_STEP / (avg_kernel_ms * 1e-3) / 1e9
+    cpu_rate, cpu_threads, cpu_steps, cpu_dt = cpu_reference_rate()
+    line = {
+        "metric": "chain-steps/s (MALA)", "value": value, "unit": "chain-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_dim": D, "n_chains_per_gpu": n, "n_chains_global": n_global,
+                   "local_steps_per_bench_step": N_LOCAL_STEPS, "parallelism": f"chains sharded x{world}, no collectives",
+                   "l2": "outputs (4.26 GB per step) >> 126 MB L2, no flush needed",
+                   "acceptance_rate": acc_rate},
+        "e2e": {"value": res_e2e[True], "unit": "chain-steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h_full,
+                "note": "TakeSerialSteps call with pinned-host initial positions in and ALL sample buffers "
+                        "(positions, log-probs, accept flags, last position) copied to pinned host memory"},
+        "e2e_device_resident_buffers": {
+            "value": res_e2e[False], "unit": "chain-steps/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": out_last.numel() * 4,
+            "note": "same call, buffers stay on the device as in the reference (jax arrays); only the "
+                    "strategy's return value (positions[:, -1]) is read back"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "flowmc::local_steps_kernel<AR1Gaussian, MALA, Layout<...>>",
+                     "algorithmic_bytes_per_launch": n * N_LOCAL_STEPS * BYTES_PER_CHAIN_STEP,
+                     "avg_launch_ms": avg_kernel_ms,
+                     "note": "bit-exact threefry2x32 makes this kernel instruction-issue bound, see DESIGN.md"},
+        "cpu_baseline": {"value": cpu_rate, "unit": "chain-steps/s", "cores": cpu_threads, "kind": "port",
+                         "sample": f"{n} chains x {cpu_steps} MALA steps ({cpu_dt:.1f} s), same target and seeds"},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -160,7 +160,11 @@ def take_serial_steps(rng_key, initial_position, target, data, kernel, n_steps, 
     for t in range(n_steps):
         k0, k1 = _split_pair(chain_keys)
         chain_keys, sub = k0, k1
+        x_in, lp_in = x, lp
         x, lp, acc, info = kernel(sub, x, lp, target, data)
+        if return_debug:
+            info.update(keys=sub.copy(), x_in=x_in.copy(), lp_in=lp_in.copy(), x_out=x.copy(), lp_out=lp.copy(),
+                        acc=acc.copy())
         if t % thinning == 0:
             pos.append(x.copy())
             lps.append(lp.copy())

@@ -9,7 +9,10 @@ the number of such chains is asserted to be tiny.
 """
 import numpy as np
 
-RTOL = 1e-5
+RTOL = 1e-5          # one kernel application on identical inputs (north_star tolerance)
+RTOL_TRAJ = 3e-4     # free-running trajectories: fp32 rounding differences (sum order, fma) are fed back
+                     # through up to ~100 steps of a nonlinear map, so they compound; the strict 1e-5
+                     # check is made per step with the oracle's state as input (teacher forcing)
 
 
 def assert_close(a, b, what, rtol=RTOL, scale=None):
@@ -26,7 +29,7 @@ def assert_close(a, b, what, rtol=RTOL, scale=None):
     assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} beyond rtol={rtol}; max err {err.max():.3e} (scale {scale:.3g})"
 
 
-def compare_chains(gpu, ora, dbg, max_diverged_frac=0.01, rtol=RTOL, tie_tol=1e-4):
+def compare_chains(gpu, ora, dbg, max_diverged_frac=0.01, rtol=RTOL_TRAJ, tie_tol=1e-4):
     """gpu/ora = (positions[n,T,d], log_probs[n,T], accepts[n,T]); dbg = per-step oracle info
     (ratio, log_u).  Returns the number of chains that diverged at a near-tie."""
     gp, gl, ga = [np.asarray(v) for v in gpu]
@@ -52,3 +55,19 @@ def compare_chains(gpu, ora, dbg, max_diverged_frac=0.01, rtol=RTOL, tie_tol=1e-
             assert_close(gl[c, :upto], ol[c, :upto], f"chain {c} log_probs", rtol, scale_l)
     assert diverged <= max(1, int(max_diverged_frac * n)), f"{diverged} of {n} chains diverged"
     return diverged
+
+
+def teacher_forced(kernel, logpdf, data, dbg, steps, rtol=RTOL, tie_tol=1e-4):
+    """Strict per-step parity: feed the oracle's state and keys at step t to the device kernel's
+    ``kernel()`` (one application) and compare with the oracle's next state."""
+    import torch
+    for t in steps:
+        info = dbg[t]
+        p, l, a = kernel.kernel(info["keys"], torch.from_numpy(info["x_in"]).cuda(),
+                                torch.from_numpy(info["lp_in"]).cuda(), logpdf, data)
+        a = a.cpu().numpy()
+        near = np.abs(info["ratio"] - info["log_u"]) <= tie_tol * np.maximum(1.0, np.abs(info["ratio"]))
+        same = a == info["acc"]
+        assert (same | near).all(), f"step {t}: accept decision differs away from a tie"
+        assert_close(p.cpu().numpy()[same], info["x_out"][same], f"step {t} positions", rtol)
+        assert_close(l.cpu().numpy()[same], info["lp_out"][same], f"step {t} log_probs", rtol)
