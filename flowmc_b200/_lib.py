@@ -25,6 +25,8 @@ class LocalParams(C.Structure):
         ("layout_hint", C.c_int),
         ("step_keys", C.c_void_p),
         ("lp0", C.c_void_p),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -51,6 +53,7 @@ def _load() -> C.CDLL:
         "flowmc_local_steps": (i32, [i32, i32, vp, u32p, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i64, i64,
                                      C.POINTER(LocalParams), u32p, vp, vp]),
         "flowmc_launch_count": (i64, []),
+        "flowmc_local_steps_workspace_bytes": (i64, [i64, i32, i32]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -10,6 +10,7 @@
 #include "../../include/flowmc_b200.h"
 #include "registry.h"
 #include "rng.cuh"
+#include "../../include/flowmc_target.cuh"
 
 namespace {
 thread_local std::string g_err;
@@ -158,6 +159,11 @@ int flowmc_random_normal(const uint32_t key[2], int64_t n, float* out, void* str
   return check_launch("random_normal");
 }
 
+int64_t flowmc_local_steps_workspace_bytes(int64_t n_chains, int d, int layout_hint) {
+  if (n_chains <= 0 || d <= 0) return 0;
+  return flowmc::local_workspace_bytes(n_chains, d, layout_hint);
+}
+
 int flowmc_local_steps(int kind, int target_id, const float* target_data, const uint32_t key[2], const float* x0,
                        float* pos_buf, float* lp_buf, float* acc_buf, int64_t n_total, int64_t cursor,
                        int64_t n_chains, int d, int n_steps, int thinning, int64_t chain_offset,
@@ -211,6 +217,8 @@ int flowmc_local_steps(int kind, int target_id, const float* target_data, const 
   a.layout_hint = params->layout_hint;
   a.step_keys = params->step_keys;
   a.lp0 = params->lp0;
+  a.workspace = params->workspace;
+  a.workspace_bytes = params->workspace_bytes;
   return vt.local_steps(kind, &a, (cudaStream_t)stream);
 }
 

@@ -13,15 +13,22 @@
 //   j = (k / VEC) * (G * VEC) + lg * VEC + (k % VEC)
 // so that a warp-wide VEC-wide store of slot block k/VEC writes G*VEC contiguous floats per chain
 // (full 32B sectors for VEC=4).  32/G chains share a warp, one warp per CTA (no CTA-level
-// synchronisation anywhere), so the grid is ceil(n_chains / (32/G)) tiny CTAs that the block
-// scheduler spreads round-robin over the 148 SMs.
+// synchronisation anywhere).
 //
 // RNG.  Per chain and step the reference consumes d+5 threefry2x32 blocks:
 //   (k_c, s) = split(k_c); (key1, key2) = split(s); z = normal(key1, (d,)); u = uniform(key2).
-// The d normals are drawn by the owning lanes (DPL independent blocks per lane -> ILP).  The
+// The d normals are drawn by the owning lanes: first all DPL blocks of a lane (branch-free, so
+// the compiler interleaves the independent 20-round chains), then the float transforms.  The
 // five key-schedule blocks are warp-uniform work, so they are batched over chunks of 32 steps:
 // the serial k_c chain runs once per chunk, then the 32 steps' (s, key1, key2, u) are computed
 // one step per lane and parked in shared memory.  Bits are identical to jax.random's.
+//
+// Time slicing.  All chains cost the same, so with more warps than resident slots a plain grid
+// runs ceil(waves) full-length waves.  Instead the step range is cut into S segments; CTA
+// (segment s, group g) -- numbered by an atomic ticket so that predecessors always start first --
+// runs steps [s*Ls, (s+1)*Ls) of group g and hands the chain state (position, cached gradient,
+// log-prob, chain key) to CTA (s+1, g) through a small global workspace guarded by a per-group
+// flag.  The host picks S to minimise ceil(groups*S/slots)*Ls; S = 1 when everything is resident.
 //
 // The gradient of the current point is carried across steps (the reference recomputes it every
 // step, MALA.py:59 -- same value, half the work).
@@ -42,6 +49,7 @@ struct Layout {
   static constexpr int kG = G, kDPL = DPL, kVEC = VEC;
   static constexpr int CPW = 32 / G;     // chains per warp
   static constexpr int DS = G * DPL;     // padded dimension (smem row length)
+  static constexpr int NSTATE = 2 * DPL + 3;  // floats per lane handed between time slices
   __device__ __forceinline__ static int dim(int k, int lg) {
     return (k / VEC) * (G * VEC) + lg * VEC + (k % VEC);
   }
@@ -68,8 +76,9 @@ __device__ __forceinline__ float group_sum(float v) {
 // One evaluation of target T at the point held in xv (slot layout L); returns logp on every lane
 // of the group and, if WANT_GRAD, the owned gradient entries in gv.
 template <class T, class L, bool WANT_GRAD>
-__device__ __forceinline__ float eval_target(const float (&xv)[L::kDPL], float (&gv)[L::kDPL], float* xrow,
-                                             float* scratch, const float* data, int d, int lg) {
+__device__ __forceinline__ float eval_target(const typename T::Consts& tc, const float (&xv)[L::kDPL],
+                                             float (&gv)[L::kDPL], float* xrow, float* scratch,
+                                             const float* data, int d, int lg) {
   constexpr int DPL = L::kDPL, VEC = L::kVEC, G = L::kG;
   // stage the point in shared memory so the target sees the whole vector
 #pragma unroll
@@ -93,17 +102,17 @@ __device__ __forceinline__ float eval_target(const float (&xv)[L::kDPL], float (
   for (int k = 0; k < DPL; ++k) {
     const int j = L::dim(k, lg);
     aux[k] = 0.0f;
-    if (j < d) aux[k] = T::partial(ctx, j, xv[k], red);
+    if (j < d) aux[k] = T::partial(tc, ctx, j, xv[k], red);
   }
   if (T::USES_SCRATCH) __syncwarp();
 #pragma unroll
   for (int r = 0; r < T::NRED; ++r) red[r] = group_sum<G>(red[r]);
-  const float lp = T::finish(ctx, red);
+  const float lp = T::finish(tc, ctx, red);
   if (WANT_GRAD) {
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
       const int j = L::dim(k, lg);
-      gv[k] = (j < d) ? T::grad(ctx, j, xv[k], aux[k], red) : 0.0f;
+      gv[k] = (j < d) ? T::grad(tc, ctx, j, xv[k], aux[k], red) : 0.0f;
     }
   }
   __syncwarp();  // xrow/scratch may be overwritten by the next evaluation
@@ -128,34 +137,102 @@ __device__ __forceinline__ void store_row(float* dst, const float (&xv)[L::kDPL]
   }
 }
 
+// z[k] = normal(key, (d,))[dim(k)] for the DPL owned dimensions (0 for padding dimensions).
+template <class L>
+__device__ __forceinline__ void draw_normals(Key key, int d, int lg, float (&z)[L::kDPL]) {
+  constexpr int DPL = L::kDPL;
+  uint32_t bits[DPL];
+#pragma unroll
+  for (int k = 0; k < DPL; ++k) bits[k] = bits_at(key, (uint64_t)L::dim(k, lg));  // branch-free: interleaves
+  bool tail = false;
+#pragma unroll
+  for (int k = 0; k < DPL; ++k) {
+    float w;
+    const float u = normal_arg(bits[k], w);
+    tail |= (w >= 5.0f);
+    z[k] = (L::dim(k, lg) < d) ? 1.41421356237309515f * (erf_inv_central(w) * u) : 0.0f;
+  }
+  if (tail) {  // |z| > ~2.9: 0.34 % of draws
+#pragma unroll
+    for (int k = 0; k < DPL; ++k) {
+      float w;
+      const float u = normal_arg(bits[k], w);
+      if (w >= 5.0f && L::dim(k, lg) < d) z[k] = 1.41421356237309515f * (erf_inv_tail(w) * u);
+    }
+  }
+}
+
+struct Slice {       // time-slicing parameters (host-computed)
+  int n_seg;         // number of segments S (1 = no slicing)
+  int seg_len;       // steps per segment
+  int n_groups;      // ceil(n_chains / CPW)
+  int* ticket;       // workspace: 1 int, zeroed before launch
+  int* flags;        // workspace: n_groups ints, zeroed before launch (segments completed per group)
+  float* state;      // workspace: n_groups * NSTATE * 32 floats
+};
+
 template <class T, int KIND, class L, int MINB>
-__global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a) {
-  constexpr int G = L::kG, DPL = L::kDPL, CPW = L::CPW, DS = L::DS;
+__global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a, const Slice sl) {
+  constexpr int G = L::kG, DPL = L::kDPL, CPW = L::CPW, DS = L::DS, NS = L::NSTATE;
   __shared__ __align__(16) WarpSmem<CPW, DS> sm;
 
   const int lane = threadIdx.x;
   const int lg = lane % G;
   const int cw = lane / G;
-  int64_t chain = (int64_t)blockIdx.x * CPW + cw;
+
+  // which (segment, group) this CTA runs: tickets are issued in start order, so the CTA that owns
+  // (seg-1, grp) has always started before this one
+  int seg = 0, grp = blockIdx.x;
+  if (sl.n_seg > 1) {
+    int tk = 0;
+    if (lane == 0) tk = atomicAdd(sl.ticket, 1);
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    seg = tk / sl.n_groups;
+    grp = tk - seg * sl.n_groups;
+  }
+  const int t_begin = seg * sl.seg_len;
+  const int t_end = min(a.n_steps, t_begin + sl.seg_len);
+
+  int64_t chain = (int64_t)grp * CPW + cw;
   const bool active = chain < a.n_chains;
   if (!active) chain = a.n_chains - 1;  // idle groups shadow the last chain; their stores are masked
   const int d = a.d;
   float* xrow = sm.xrow[cw];
   float* scratch = sm.scratch[cw];
+  const typename T::Consts tc = T::prepare(a.data, d);
 
-  // per-chain key: split(subkey, n_chains_global)[global chain index]   (take_steps.py:72)
-  Key kc = split_at(a.subkey, (uint64_t)(a.chain_offset + chain));
-
-  float x[DPL], g[DPL];
+  Key kc;
+  float x[DPL], g[DPL], lp;
+  if (seg == 0) {
+    // per-chain key: split(subkey, n_chains_global)[global chain index]   (take_steps.py:72)
+    kc = split_at(a.subkey, (uint64_t)(a.chain_offset + chain));
 #pragma unroll
-  for (int k = 0; k < DPL; ++k) {
-    const int j = L::dim(k, lg);
-    x[k] = (j < d) ? a.x0[chain * d + j] : 0.0f;
-    g[k] = 0.0f;
+    for (int k = 0; k < DPL; ++k) {
+      const int j = L::dim(k, lg);
+      x[k] = (j < d) ? a.x0[chain * d + j] : 0.0f;
+      g[k] = 0.0f;
+    }
+    // logpdf(initial_position) seeds the scan carry (take_steps.py:177); MALA/HMC cache the gradient
+    lp = eval_target<T, L, KIND != KIND_GRW>(tc, x, g, xrow, scratch, a.data, d, lg);
+    if (a.lp0 != nullptr) lp = a.lp0[chain];  // ProposalBase.kernel(): caller-supplied log_prob
+  } else {
+    // wait for the previous time slice of this group, then pick up its state
+    if (lane == 0) {
+      const volatile int* f = sl.flags + grp;
+      while (*f < seg) __nanosleep(200);
+    }
+    __syncwarp();
+    __threadfence();
+    const float* st = sl.state + ((int64_t)grp * NS) * 32 + lane;
+#pragma unroll
+    for (int k = 0; k < DPL; ++k) {
+      x[k] = __ldcg(st + k * 32);
+      g[k] = __ldcg(st + (DPL + k) * 32);
+    }
+    lp = __ldcg(st + (2 * DPL) * 32);
+    kc.k0 = __float_as_uint(__ldcg(st + (2 * DPL + 1) * 32));
+    kc.k1 = __float_as_uint(__ldcg(st + (2 * DPL + 2) * 32));
   }
-  // logpdf(initial_position) seeds the scan carry (take_steps.py:177); MALA/HMC also cache the gradient
-  float lp = eval_target<T, L, KIND != KIND_GRW>(x, g, xrow, scratch, a.data, d, lg);
-  if (a.lp0 != nullptr) lp = a.lp0[chain];  // ProposalBase.kernel(): caller-supplied log_prob
 
   const float dt = a.step_size;
   const float dt2 = dt * dt;
@@ -178,9 +255,11 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
 
   const int thin = a.thinning;
   const int t_last_stored = ((a.n_steps - 1) / thin) * thin;
+  int o_next = (t_begin + thin - 1) / thin;  // next output index
+  int t_next = o_next * thin;                // ... and the step that produces it
 
-  for (int t0 = 0; t0 < a.n_steps; t0 += kChunk) {
-    const int nb = min(kChunk, a.n_steps - t0);
+  for (int t0 = t_begin; t0 < t_end; t0 += kChunk) {
+    const int nb = min(kChunk, t_end - t0);
     // ---- key schedule for this chunk -------------------------------------------------
     // serial part: k_c^{t+1} = split(k_c^t)[0]   (take_steps.py:158)
     for (int t = 0; t < nb; ++t) {
@@ -198,7 +277,7 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
       Key kt{sm.k0[c][lane], sm.k1[c][lane]};
       Key s = split_at(kt, 1);
       if (a.step_keys != nullptr) {  // single kernel() call with explicit per-chain keys
-        const int64_t ch = min((int64_t)blockIdx.x * CPW + c, a.n_chains - 1);
+        const int64_t ch = min((int64_t)grp * CPW + c, a.n_chains - 1);
         s = Key{a.step_keys[2 * ch], a.step_keys[2 * ch + 1]};
       }
       Key key1 = split_at(s, 0);
@@ -210,7 +289,7 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
     }
     __syncwarp();
 
-    const int o_first = (t0 + thin - 1) / thin;  // first output index of this chunk
+    const int o_first = o_next;  // first output index of this chunk
     // ---- steps ---------------------------------------------------------------------------
     for (int tt = 0; tt < nb; ++tt) {
       const int t = t0 + tt;
@@ -220,20 +299,16 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
 
       if (KIND == KIND_MALA) {
         float prop[DPL], g1[DPL];
+        draw_normals<L>(key1, d, lg, prop);  // prop holds z for now
         float qa = 0.0f;
 #pragma unroll
         for (int k = 0; k < DPL; ++k) {
-          const int j = L::dim(k, lg);
-          prop[k] = 0.0f;
-          if (j < d) {
-            const float z = bits_to_normal(bits_at(key1, (uint64_t)j));
-            const float mean = x[k] + (dt2 * g[k]) / 2.0f;  // MALA.py:60
-            prop[k] = mean + dt * z;                        // MALA.py:61-63
-            const float y = prop[k] - mean;
-            qa += y * y;
-          }
+          const float mean = x[k] + (dt2 * g[k]) / 2.0f;  // MALA.py:60
+          prop[k] = mean + dt * prop[k];                  // MALA.py:61-63
+          const float y = prop[k] - mean;
+          qa += y * y;
         }
-        const float lp1 = eval_target<T, L, true>(prop, g1, xrow, scratch, a.data, d, lg);
+        const float lp1 = eval_target<T, L, true>(tc, prop, g1, xrow, scratch, a.data, d, lg);
         float qb = 0.0f;
 #pragma unroll
         for (int k = 0; k < DPL; ++k) {
@@ -255,35 +330,26 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
         lp = acc ? lp1 : lp;
       } else if (KIND == KIND_GRW) {
         float prop[DPL], g1[DPL];
+        draw_normals<L>(key1, d, lg, prop);
 #pragma unroll
-        for (int k = 0; k < DPL; ++k) {
-          const int j = L::dim(k, lg);
-          prop[k] = 0.0f;
-          if (j < d) {
-            const float z = bits_to_normal(bits_at(key1, (uint64_t)j));
-            prop[k] = x[k] + z * dt;  // Gaussian_random_walk.py:49-52
-          }
-        }
-        const float lp1 = eval_target<T, L, false>(prop, g1, xrow, scratch, a.data, d, lg);
+        for (int k = 0; k < DPL; ++k) prop[k] = x[k] + prop[k] * dt;  // Gaussian_random_walk.py:49-52
+        const float lp1 = eval_target<T, L, false>(tc, prop, g1, xrow, scratch, a.data, d, lg);
         acc = logu < (lp1 - lp);  // Gaussian_random_walk.py:56
 #pragma unroll
         for (int k = 0; k < DPL; ++k) x[k] = acc ? prop[k] : x[k];
         lp = acc ? lp1 : lp;
       } else {  // HMC
         float xs[DPL], p[DPL], g1[DPL];
+        draw_normals<L>(key1, d, lg, p);
         // momentum = normal(key1) @ chol(inv(M)).T   (HMC.py:133-136)
         if (a.hmc_diag) {
 #pragma unroll
-          for (int k = 0; k < DPL; ++k) {
-            const int j = L::dim(k, lg);
-            p[k] = 0.0f;
-            if (j < d) p[k] = bits_to_normal(bits_at(key1, (uint64_t)j)) * ld[k];
-          }
+          for (int k = 0; k < DPL; ++k) p[k] = p[k] * ld[k];
         } else {
 #pragma unroll
           for (int k = 0; k < DPL; ++k) {
             const int j = L::dim(k, lg);
-            if (j < d) scratch[j] = bits_to_normal(bits_at(key1, (uint64_t)j));
+            if (j < d) scratch[j] = p[k];
           }
           __syncwarp();
 #pragma unroll
@@ -317,7 +383,7 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
           const float c1 = (it == a.n_leapfrog + 1) ? 0.5f : 1.0f;
 #pragma unroll
           for (int k = 0; k < DPL; ++k) xs[k] = xs[k] + (eps * 1.0f) * (p[k] * cs[k]);
-          lp1 = eval_target<T, L, true>(xs, g1, xrow, scratch, a.data, d, lg);
+          lp1 = eval_target<T, L, true>(tc, xs, g1, xrow, scratch, a.data, d, lg);
 #pragma unroll
           for (int k = 0; k < DPL; ++k) p[k] = p[k] - (eps * c1) * (-g1[k]);
         }
@@ -336,23 +402,23 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
       }
 
       // ---- outputs (take_steps.py:134-142): thinned, written in place at the cursor ----------
-      if (t % thin == 0) {
-        const int64_t o = t / thin;
-        if (active) store_row<L>(a.pos_buf + (chain * a.n_total + a.cursor + o) * d, x, d, lg);
+      if (t == t_next) {
+        if (active) store_row<L>(a.pos_buf + (chain * a.n_total + a.cursor + o_next) * d, x, d, lg);
         if (lg == 0) {
-          sm.lpst[cw][o - o_first] = lp;
-          sm.accst[cw][o - o_first] = acc ? 1.0f : 0.0f;
+          sm.lpst[cw][o_next - o_first] = lp;
+          sm.accst[cw][o_next - o_first] = acc ? 1.0f : 0.0f;
         }
         if (t == t_last_stored && active) store_row<L>(a.last_pos + chain * d, x, d, lg);
+        ++o_next;
+        t_next += thin;
       }
     }
     __syncwarp();
     // flush this chunk's log-probs and accept flags: one coalesced row per chain
-    const int o_end = (t0 + nb + thin - 1) / thin;  // one past the last output index of the chunk
-    const int n_out = o_end - o_first;
+    const int n_out = o_next - o_first;
 #pragma unroll
     for (int c = 0; c < CPW; ++c) {
-      const int64_t ch = (int64_t)blockIdx.x * CPW + c;
+      const int64_t ch = (int64_t)grp * CPW + c;
       if (ch < a.n_chains && lane < n_out) {
         const int64_t off = ch * a.n_total + a.cursor + o_first + lane;
         __stcs(a.lp_buf + off, sm.lpst[c][lane]);
@@ -360,6 +426,21 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
       }
     }
     __syncwarp();
+  }
+
+  if (t_end < a.n_steps) {  // hand the chain state to the next time slice
+    float* st = sl.state + ((int64_t)grp * NS) * 32 + lane;
+#pragma unroll
+    for (int k = 0; k < DPL; ++k) {
+      __stcg(st + k * 32, x[k]);
+      __stcg(st + (DPL + k) * 32, g[k]);
+    }
+    __stcg(st + (2 * DPL) * 32, lp);
+    __stcg(st + (2 * DPL + 1) * 32, __uint_as_float(kc.k0));
+    __stcg(st + (2 * DPL + 2) * 32, __uint_as_float(kc.k1));
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(sl.flags + grp, seg + 1);
   }
 }
 
@@ -375,6 +456,7 @@ __global__ void __launch_bounds__(32) target_eval_kernel(const float* __restrict
   int64_t i = (int64_t)blockIdx.x * CPW + cw;
   const bool active = i < n;
   if (!active) i = n - 1;
+  const typename T::Consts tc = T::prepare(data, d);
   float x[DPL], g[DPL];
 #pragma unroll
   for (int k = 0; k < DPL; ++k) {
@@ -384,9 +466,9 @@ __global__ void __launch_bounds__(32) target_eval_kernel(const float* __restrict
   }
   float lp;
   if (grad_out != nullptr) {
-    lp = eval_target<T, L, true>(x, g, xrow[cw], scratch[cw], data, d, lg);
+    lp = eval_target<T, L, true>(tc, x, g, xrow[cw], scratch[cw], data, d, lg);
   } else {
-    lp = eval_target<T, L, false>(x, g, xrow[cw], scratch[cw], data, d, lg);
+    lp = eval_target<T, L, false>(tc, x, g, xrow[cw], scratch[cw], data, d, lg);
   }
   if (active) {
     if (lg == 0) lp_out[i] = lp;
@@ -422,8 +504,8 @@ __host__ inline int pick_layout(int d, int hint) {
   }
   if (d % 4 == 0) {
     if (d <= 32) return 4;
-    if (d <= 64) return 5;
-    if (d <= 128) return 7;
+    if (d <= 64) return 6;
+    if (d <= 128) return 8;
     if (d <= 256) return 10;
     if (d <= 512) return 12;
     return -1;
@@ -435,11 +517,64 @@ __host__ inline int pick_layout(int d, int hint) {
   return -1;
 }
 
+// bytes of workspace flowmc_local_steps needs for time slicing with the layout it would pick
+__host__ inline int64_t local_workspace_bytes(int64_t n_chains, int d, int hint) {
+  const int li = pick_layout(d, hint);
+  if (li < 0) return 0;
+  const LayoutInfo L = layout_info(li);
+  const int64_t cpw = 32 / L.G;
+  const int64_t n_groups = (n_chains + cpw - 1) / cpw;
+  const int64_t head = 256 + ((n_groups * 4 + 255) / 256) * 256;
+  return head + n_groups * (2 * L.DPL + 3) * 32 * 4;
+}
+
 template <class T, int KIND, int G, int DPL, int VEC, int MINB>
 inline int launch_local_one(const LocalArgs* a, cudaStream_t stream) {
   using L = Layout<G, DPL, VEC>;
-  const int64_t nblk = (a->n_chains + L::CPW - 1) / L::CPW;
-  local_steps_kernel<T, KIND, L, MINB><<<(unsigned)nblk, 32, 0, stream>>>(*a);
+  auto kern = local_steps_kernel<T, KIND, L, MINB>;
+  const int64_t n_groups = (a->n_chains + L::CPW - 1) / L::CPW;
+  Slice sl{1, a->n_steps, (int)n_groups, nullptr, nullptr, nullptr};
+
+  // resident slots for this kernel (cached per instantiation)
+  static int slots = 0;
+  if (slots == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, 0);
+    slots = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  const int64_t head = 256 + ((n_groups * 4 + 255) / 256) * 256;
+  const int64_t need = head + n_groups * L::NSTATE * 32 * 4;
+  const int max_seg = a->n_steps / kChunk;  // keep segments >= one key-schedule chunk
+  if (n_groups > slots && max_seg >= 2 && a->workspace != nullptr && a->workspace_bytes >= need &&
+      a->step_keys == nullptr) {
+    // choose S minimising (rounds of resident CTAs) x (segment length)
+    int64_t best_cost = ((n_groups + slots - 1) / slots) * (int64_t)a->n_steps;
+    int best_s = 1, best_len = a->n_steps;
+    for (int s = 2; s <= (max_seg < 48 ? max_seg : 48); ++s) {
+      const int len = (a->n_steps + s - 1) / s;
+      const int s_eff = (a->n_steps + len - 1) / len;
+      const int64_t rounds = (n_groups * s_eff + slots - 1) / slots;
+      const int64_t cost = rounds * (len + 2);  // +2: per-slice hand-off overhead in step units
+      if (cost < best_cost) {
+        best_cost = cost;
+        best_s = s_eff;
+        best_len = len;
+      }
+    }
+    if (best_s > 1) {
+      char* ws = static_cast<char*>(a->workspace);
+      sl.n_seg = best_s;
+      sl.seg_len = best_len;
+      sl.ticket = reinterpret_cast<int*>(ws);
+      sl.flags = reinterpret_cast<int*>(ws + 256);
+      sl.state = reinterpret_cast<float*>(ws + head);
+      cudaMemsetAsync(ws, 0, (size_t)head, stream);
+    }
+  }
+  const int64_t nblk = n_groups * sl.n_seg;
+  kern<<<(unsigned)nblk, 32, 0, stream>>>(*a, sl);
   flowmc_count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

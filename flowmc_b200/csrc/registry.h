@@ -32,6 +32,8 @@ struct LocalArgs {
   int layout_hint;
   const uint32_t* step_keys;  // optional [n_chains,2]; n_steps must be 1
   const float* lp0;           // optional [n_chains]
+  void* workspace;            // optional: time-slicing scratch (see local_steps.cuh)
+  int64_t workspace_bytes;
 };
 
 }  // namespace flowmc

@@ -73,44 +73,52 @@ __device__ __forceinline__ float bits_to_unit(uint32_t bits) {
 // jax.random.uniform(key) with minval=0, maxval=1
 __device__ __forceinline__ float bits_to_uniform01(uint32_t bits) { return fmaxf(0.0f, bits_to_unit(bits)); }
 
-// XLA ErfInv32 (Giles' single-precision polynomial).  w = -log1p(-x*x) is evaluated as
-// -ln2 * lg2(1 - x*x) with a single-rounding fma for the argument: the result enters the
-// polynomial only through (w - 2.5) or (sqrt(w) - 3), so an absolute error of a few 1e-7 in w
-// moves the output by < 1 ulp-equivalent (checked against the oracle in tests/test_gpu_rng.py).
-__device__ __forceinline__ float erf_inv32(float x) {
-  float w = -0.6931471805599453f * __log2f(fmaf(-x, x, 1.0f));
-  float p;
-  if (w < 5.0f) {
-    w -= 2.5f;
-    p = 2.81022636e-08f;
-    p = fmaf(p, w, 3.43273939e-07f);
-    p = fmaf(p, w, -3.5233877e-06f);
-    p = fmaf(p, w, -4.39150654e-06f);
-    p = fmaf(p, w, 0.00021858087f);
-    p = fmaf(p, w, -0.00125372503f);
-    p = fmaf(p, w, -0.00417768164f);
-    p = fmaf(p, w, 0.246640727f);
-    p = fmaf(p, w, 1.50140941f);
-  } else {
-    w = sqrtf(w) - 3.0f;
-    p = -0.000200214257f;
-    p = fmaf(p, w, 0.000100950558f);
-    p = fmaf(p, w, 0.00134934322f);
-    p = fmaf(p, w, -0.00367342844f);
-    p = fmaf(p, w, 0.00573950773f);
-    p = fmaf(p, w, -0.0076224613f);
-    p = fmaf(p, w, 0.00943887047f);
-    p = fmaf(p, w, 1.00167406f);
-    p = fmaf(p, w, 2.83297682f);
-  }
-  return p * x;
+// XLA ErfInv32 (Giles' single-precision polynomial): w = -log1p(-x*x); w < 5 ? P1(w - 2.5) : P2(sqrt(w) - 3);
+// result p * x.  x*x is rounded on its own (as XLA's multiply op does) and log1p(y) is evaluated
+// as ln2 * lg2(1 + y): 1 + y is exact for |x| >= 0.71 and otherwise off by < 3e-8, and w enters
+// the polynomials only through (w - 2.5) / (sqrt(w) - 3), so the result agrees with the oracle's
+// libm evaluation to ~1e-6 relative (tests/test_gpu_rng.py).  The three pieces are separate so
+// that callers can run the branch-free central polynomial on every draw and patch the rare tail.
+__device__ __forceinline__ float normal_arg(uint32_t bits, float& w) {
+  const float lo = -0.99999994f;  // nextafter(-1, 0): jax.random.normal's uniform minval
+  const float u = fmaxf(lo, fmaf(bits_to_unit(bits), 2.0f, lo));
+  const float xx = __fmul_rn(u, u);
+  w = -0.6931471805599453f * __log2f(1.0f - xx);
+  return u;
+}
+__device__ __forceinline__ float erf_inv_central(float w) {
+  w -= 2.5f;
+  float p = 2.81022636e-08f;
+  p = fmaf(p, w, 3.43273939e-07f);
+  p = fmaf(p, w, -3.5233877e-06f);
+  p = fmaf(p, w, -4.39150654e-06f);
+  p = fmaf(p, w, 0.00021858087f);
+  p = fmaf(p, w, -0.00125372503f);
+  p = fmaf(p, w, -0.00417768164f);
+  p = fmaf(p, w, 0.246640727f);
+  p = fmaf(p, w, 1.50140941f);
+  return p;
+}
+__device__ __forceinline__ float erf_inv_tail(float w) {
+  w = sqrtf(w) - 3.0f;
+  float p = -0.000200214257f;
+  p = fmaf(p, w, 0.000100950558f);
+  p = fmaf(p, w, 0.00134934322f);
+  p = fmaf(p, w, -0.00367342844f);
+  p = fmaf(p, w, 0.00573950773f);
+  p = fmaf(p, w, -0.0076224613f);
+  p = fmaf(p, w, 0.00943887047f);
+  p = fmaf(p, w, 1.00167406f);
+  p = fmaf(p, w, 2.83297682f);
+  return p;
 }
 
 // jax.random.normal: sqrt(2) * erf_inv(uniform(minval=nextafter(-1,0), maxval=1))
 __device__ __forceinline__ float bits_to_normal(uint32_t bits) {
-  const float lo = -0.99999994f;
-  float u = fmaxf(lo, fmaf(bits_to_unit(bits), 2.0f, lo));
-  return 1.41421356237309515f * erf_inv32(u);
+  float w;
+  const float u = normal_arg(bits, w);
+  const float p = (w < 5.0f) ? erf_inv_central(w) : erf_inv_tail(w);
+  return 1.41421356237309515f * (p * u);
 }
 #endif
 

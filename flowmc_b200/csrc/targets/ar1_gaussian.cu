@@ -6,18 +6,25 @@
 struct AR1Gaussian {
   static constexpr int NRED = 1;
   static constexpr bool USES_SCRATCH = false;
-  __device__ static float partial(const flowmc::TargetCtx& c, int j, float xj, float* red) {
-    const float rho = c.data[0];
-    const float a = 1.0f / (1.0f - rho * rho);
-    const float left = (j > 0) ? c.x[j - 1] : 0.0f;
-    const float right = (j < c.d - 1) ? c.x[j + 1] : 0.0f;
-    const float diag = (j > 0 && j < c.d - 1) ? 1.0f + rho * rho : 1.0f;
-    const float px = a * (diag * xj - rho * (left + right));
+  struct Consts {
+    float rho, a, dmid;
+  };
+  __device__ static Consts prepare(const float* data, int d) {
+    const float rho = data[0];
+    return Consts{rho, 1.0f / (1.0f - rho * rho), 1.0f + rho * rho};
+  }
+  __device__ static float partial(const Consts& k, const flowmc::TargetCtx& c, int j, float xj, float* red) {
+    const bool lo = j > 0, hi = j < c.d - 1;
+    const float left = lo ? c.x[j - 1] : 0.0f;
+    const float right = hi ? c.x[j + 1] : 0.0f;
+    const float diag = (lo && hi) ? k.dmid : 1.0f;
+    const float px = k.a * (diag * xj - k.rho * (left + right));
     red[0] += xj * px;
     return px;
   }
-  __device__ static float finish(const flowmc::TargetCtx& c, float* red) { return -0.5f * red[0]; }
-  __device__ static float grad(const flowmc::TargetCtx& c, int j, float xj, float aux, const float* red) {
+  __device__ static float finish(const Consts& k, const flowmc::TargetCtx& c, float* red) { return -0.5f * red[0]; }
+  __device__ static float grad(const Consts& k, const flowmc::TargetCtx& c, int j, float xj, float aux,
+                               const float* red) {
     return -aux;
   }
 };

@@ -6,8 +6,12 @@
 struct DualMoon {
   static constexpr int NRED = 1;
   static constexpr bool USES_SCRATCH = false;
-  __device__ static float partial(const flowmc::TargetCtx& c, int j, float xj, float* red) {
-    const float r = xj - c.data[j];
+  struct Consts {
+    const float* mu;
+  };
+  __device__ static Consts prepare(const float* data, int d) { return Consts{data}; }
+  __device__ static float partial(const Consts& k, const flowmc::TargetCtx& c, int j, float xj, float* red) {
+    const float r = xj - __ldg(k.mu + j);
     red[0] += r * r;
     return r;
   }
@@ -20,8 +24,8 @@ struct DualMoon {
     lse = m + logf(s);
     dlse = (ea * (-a / w) + eb * (-b / w)) / s;
   }
-  // red out: [0] = -(t/0.1)/|r|  (radial gradient factor); dlse terms are recomputed by owners
-  __device__ static float finish(const flowmc::TargetCtx& c, float* red) {
+  // red out: [0] = -(t/0.1)/|r|  (radial gradient factor)
+  __device__ static float finish(const Consts& k, const flowmc::TargetCtx& c, float* red) {
     const float nrm = sqrtf(red[0]);
     const float t = (nrm - 2.0f) / 0.1f;
     float l2, d2, l3, d3;
@@ -30,7 +34,8 @@ struct DualMoon {
     red[0] = -(t / 0.1f) / nrm;
     return -(0.5f * t * t - l2 - l3);
   }
-  __device__ static float grad(const flowmc::TargetCtx& c, int j, float xj, float aux, const float* red) {
+  __device__ static float grad(const Consts& k, const flowmc::TargetCtx& c, int j, float xj, float aux,
+                               const float* red) {
     float gj = red[0] * aux;
     if (j < 2) {
       float l, dl;

@@ -7,46 +7,51 @@ struct GaussianMixture {
   static constexpr int KMAX = 8;
   static constexpr int NRED = KMAX;
   static constexpr bool USES_SCRATCH = false;
-  __device__ static float partial(const flowmc::TargetCtx& c, int j, float xj, float* red) {
-    const int K = (int)c.data[0];
-    const float* mu = c.data + 2 + K + j;
+  struct Consts {
+    int K;
+    float iv;
+    const float* logw;
+    const float* mu;
+  };
+  __device__ static Consts prepare(const float* data, int d) {
+    const int K = (int)data[0];
+    return Consts{K, data[1], data + 2, data + 2 + K};
+  }
+  __device__ static float partial(const Consts& k, const flowmc::TargetCtx& c, int j, float xj, float* red) {
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k < K) {
-        const float r = __ldg(mu + (int64_t)k * c.d) - xj;
-        red[k] += r * r;
+    for (int m = 0; m < KMAX; ++m) {
+      if (m < k.K) {
+        const float r = __ldg(k.mu + (int64_t)m * c.d + j) - xj;
+        red[m] += r * r;
       }
     }
     return 0.0f;
   }
   // red out: softmax weights
-  __device__ static float finish(const flowmc::TargetCtx& c, float* red) {
-    const int K = (int)c.data[0];
-    const float iv = c.data[1];
-    float m = -INFINITY;
+  __device__ static float finish(const Consts& k, const flowmc::TargetCtx& c, float* red) {
+    float mx = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      red[k] = (k < K) ? c.data[2 + k] - 0.5f * iv * red[k] : -INFINITY;
-      m = fmaxf(m, red[k]);
+    for (int m = 0; m < KMAX; ++m) {
+      red[m] = (m < k.K) ? __ldg(k.logw + m) - 0.5f * k.iv * red[m] : -INFINITY;
+      mx = fmaxf(mx, red[m]);
     }
     float s = 0.0f;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      red[k] = (k < K) ? expf(red[k] - m) : 0.0f;
-      s += red[k];
+    for (int m = 0; m < KMAX; ++m) {
+      red[m] = (m < k.K) ? expf(red[m] - mx) : 0.0f;
+      s += red[m];
     }
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) red[k] = red[k] / s;
-    return m + logf(s);
+    for (int m = 0; m < KMAX; ++m) red[m] = red[m] / s;
+    return mx + logf(s);
   }
-  __device__ static float grad(const flowmc::TargetCtx& c, int j, float xj, float aux, const float* red) {
-    const int K = (int)c.data[0];
-    const float* mu = c.data + 2 + K + j;
+  __device__ static float grad(const Consts& k, const flowmc::TargetCtx& c, int j, float xj, float aux,
+                               const float* red) {
     float gj = 0.0f;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k)
-      if (k < K) gj += red[k] * (__ldg(mu + (int64_t)k * c.d) - xj);
-    return c.data[1] * gj;
+    for (int m = 0; m < KMAX; ++m)
+      if (m < k.K) gj += red[m] * (__ldg(k.mu + (int64_t)m * c.d + j) - xj);
+    return k.iv * gj;
   }
 };
 FLOWMC_REGISTER_TARGET(GaussianMixture, "gaussian_mixture")

@@ -7,14 +7,20 @@
 struct IsoGaussian {
   static constexpr int NRED = 1;
   static constexpr bool USES_SCRATCH = false;
-  __device__ static float partial(const flowmc::TargetCtx& c, int j, float xj, float* red) {
-    const float r = xj - c.data[1 + j];
+  struct Consts {
+    float c;
+    const float* mu;
+  };
+  __device__ static Consts prepare(const float* data, int d) { return Consts{data[0], data + 1}; }
+  __device__ static float partial(const Consts& k, const flowmc::TargetCtx& c, int j, float xj, float* red) {
+    const float r = xj - __ldg(k.mu + j);
     red[0] += r * r;
     return r;
   }
-  __device__ static float finish(const flowmc::TargetCtx& c, float* red) { return -c.data[0] * red[0]; }
-  __device__ static float grad(const flowmc::TargetCtx& c, int j, float xj, float aux, const float* red) {
-    return -2.0f * c.data[0] * aux;
+  __device__ static float finish(const Consts& k, const flowmc::TargetCtx& c, float* red) { return -k.c * red[0]; }
+  __device__ static float grad(const Consts& k, const flowmc::TargetCtx& c, int j, float xj, float aux,
+                               const float* red) {
+    return -2.0f * k.c * aux;
   }
 };
 FLOWMC_REGISTER_TARGET(IsoGaussian, "iso_gaussian")

@@ -5,7 +5,9 @@
 struct Rosenbrock {
   static constexpr int NRED = 1;
   static constexpr bool USES_SCRATCH = false;
-  __device__ static float partial(const flowmc::TargetCtx& c, int j, float xj, float* red) {
+  struct Consts {};
+  __device__ static Consts prepare(const float* data, int d) { return Consts{}; }
+  __device__ static float partial(const Consts& k, const flowmc::TargetCtx& c, int j, float xj, float* red) {
     float gj = 0.0f;
     if (j < c.d - 1) {
       const float u = c.x[j + 1] - xj * xj;
@@ -20,8 +22,9 @@ struct Rosenbrock {
     }
     return gj;
   }
-  __device__ static float finish(const flowmc::TargetCtx& c, float* red) { return -red[0]; }
-  __device__ static float grad(const flowmc::TargetCtx& c, int j, float xj, float aux, const float* red) {
+  __device__ static float finish(const Consts& k, const flowmc::TargetCtx& c, float* red) { return -red[0]; }
+  __device__ static float grad(const Consts& k, const flowmc::TargetCtx& c, int j, float xj, float aux,
+                               const float* red) {
     return aux;
   }
 };

@@ -53,6 +53,7 @@ class TakeSteps(Strategy):
         self.verbose = verbose
         # global chain shard owned by this process: (offset, n_chains_global) or None = all chains
         self.chain_shard = None
+        self._workspace = None
 
     def set_current_position(self, current_position: int):
         self.current_position = current_position
@@ -115,6 +116,11 @@ class TakeSerialSteps(TakeSteps):
         n_total = pos_b.data.shape[1]
         offset, n_glob = self.chain_shard if self.chain_shard is not None else (0, n)
         params, keep = kernel._local_params(d, dev)
+        ws_bytes = int(lib.flowmc_local_steps_workspace_bytes(n, d, params.layout_hint))
+        if self._workspace is None or self._workspace.numel() < ws_bytes or self._workspace.device != dev:
+            self._workspace = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        params.workspace = self._workspace.data_ptr()
+        params.workspace_bytes = self._workspace.numel()
         pk = logpdf.target.packed_on(data, d, dev)
         key = np.ascontiguousarray(rng_key, dtype=np.uint32)
         key_out = np.zeros(2, np.uint32)

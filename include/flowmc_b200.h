@@ -91,7 +91,14 @@ typedef struct FlowmcLocalParams {
                               * n_steps == 1; the key is used exactly as kernel()'s rng_key argument */
   const float* lp0;       /* optional, device [n_chains]: incoming log_prob (kernel()'s log_prob
                            * argument); NULL = logpdf(x0) as in take_steps.py:177 */
+  void* workspace;        /* optional, device: scratch for time slicing (chain-state hand-off between
+                           * CTAs when there are more chain groups than resident slots); size from
+                           * flowmc_local_steps_workspace_bytes().  NULL = plain one-CTA-per-group grid */
+  int64_t workspace_bytes;
 } FlowmcLocalParams;
+
+/* bytes of `workspace` that flowmc_local_steps can use for (n_chains, d, layout_hint) */
+FLOWMC_API int64_t flowmc_local_steps_workspace_bytes(int64_t n_chains, int d, int layout_hint);
 
 /* Runs n_steps of one local kernel for n_chains chains in ONE persistent kernel launch and
  * writes the thinned samples straight into the (chain-major) sampler buffers at `cursor`:

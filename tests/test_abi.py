@@ -43,3 +43,14 @@ def test_python_callable_is_rejected():
     from flowmc_b200.resource.logPDF import LogPDF
     with pytest.raises(TypeError):
         LogPDF(lambda x, data: -0.5 * (x ** 2).sum(), n_dims=3)
+
+
+def test_user_plugin_compiles_and_registers(tmp_path):
+    """A target written against include/flowmc_target.cuh builds into its own .so and registers
+    itself on load (no GPU needed: nvcc cross-compiles, registration is a host-side table)."""
+    from test_gpu_targets import QUARTIC_PLUGIN
+    from flowmc_b200 import targets as T
+    from flowmc_b200._lib import lib
+    tgt = T.compile_target(QUARTIC_PLUGIN, "test_quartic", lambda data, d: np.array([0.25], np.float32),
+                           str(tmp_path))
+    assert lib.flowmc_target_lookup(b"test_quartic") == tgt.target_id >= 6

@@ -8,6 +8,24 @@ from parity import assert_close
 pytestmark = pytest.mark.gpu
 
 
+QUARTIC_PLUGIN = r'''
+#include "flowmc_target.cuh"
+// logp = -c * sum x^4, data = [c]
+struct Quartic {
+  static constexpr int NRED = 1;
+  static constexpr bool USES_SCRATCH = false;
+  struct Consts { float c; };
+  __device__ static Consts prepare(const float* data, int d) { return Consts{data[0]}; }
+  __device__ static float partial(const Consts& k, const flowmc::TargetCtx& c, int j, float xj, float* red) {
+    red[0] += k.c * xj * xj * xj * xj; return xj; }
+  __device__ static float finish(const Consts& k, const flowmc::TargetCtx& c, float* red) { return -red[0]; }
+  __device__ static float grad(const Consts& k, const flowmc::TargetCtx& c, int j, float xj, float aux,
+                               const float* red) { return -4.0f * k.c * aux * aux * aux; }
+};
+FLOWMC_REGISTER_TARGET(Quartic, "test_quartic")
+'''
+
+
 def _cases():
     from flowmc_b200 import targets as T
     from oracle import targets as O
@@ -58,19 +76,7 @@ def test_dual_moon_known_answer(cuda):
 def test_user_plugin_roundtrip(cuda, tmp_path):
     # a target written against include/flowmc_target.cuh, compiled and registered at run time
     from flowmc_b200 import targets as T
-    src = r'''
-#include "flowmc_target.cuh"
-struct Quartic {
-  static constexpr int NRED = 1;
-  static constexpr bool USES_SCRATCH = false;
-  __device__ static float partial(const flowmc::TargetCtx& c, int j, float xj, float* red) {
-    red[0] += c.data[0] * xj * xj * xj * xj; return xj; }
-  __device__ static float finish(const flowmc::TargetCtx& c, float* red) { return -red[0]; }
-  __device__ static float grad(const flowmc::TargetCtx& c, int j, float xj, float aux, const float* red) {
-    return -4.0f * c.data[0] * aux * aux * aux; }
-};
-FLOWMC_REGISTER_TARGET(Quartic, "test_quartic")
-'''
+    src = QUARTIC_PLUGIN
     tgt = T.compile_target(src, "test_quartic", lambda data, d: np.array([0.25], np.float32), str(tmp_path))
     x = torch.randn(50, 12, device=cuda)
     lp, g = tgt.evaluate(x, None, want_grad=True)
