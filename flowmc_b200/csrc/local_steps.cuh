@@ -44,9 +44,12 @@ enum : int { KIND_MALA = 0, KIND_HMC = 1, KIND_GRW = 2 };
 
 constexpr int kChunk = 32;  // steps per key-schedule chunk (= one step per lane)
 
-template <int G, int DPL, int VEC>
+// PAD = false promises d == G * DPL (no padding dimensions): every `j < d` test folds away.
+template <int G, int DPL, int VEC, bool PAD = true>
 struct Layout {
   static constexpr int kG = G, kDPL = DPL, kVEC = VEC;
+  static constexpr bool kPAD = PAD;
+  __device__ __forceinline__ static bool valid(int j, int d) { return !PAD || j < d; }
   static constexpr int CPW = 32 / G;     // chains per warp
   static constexpr int DS = G * DPL;     // padded dimension (smem row length)
   static constexpr int NSTATE = 2 * DPL + 3;  // floats per lane handed between time slices
@@ -55,9 +58,11 @@ struct Layout {
   }
 };
 
+constexpr int kHalo = 4;  // zero floats kept before x[0] and after x[DS-1] (x[-1] == x[d] == 0 for targets)
+
 template <int CPW, int DS>
 struct WarpSmem {
-  float xrow[CPW][DS];
+  float xrow[CPW][DS + 2 * kHalo];
   float scratch[CPW][DS];
   uint32_t k0[CPW][kChunk];
   uint32_t k1[CPW][kChunk];
@@ -102,7 +107,7 @@ __device__ __forceinline__ float eval_target(const typename T::Consts& tc, const
   for (int k = 0; k < DPL; ++k) {
     const int j = L::dim(k, lg);
     aux[k] = 0.0f;
-    if (j < d) aux[k] = T::partial(tc, ctx, j, xv[k], red);
+    if (L::valid(j, d)) aux[k] = T::partial(tc, ctx, j, xv[k], red);
   }
   if (T::USES_SCRATCH) __syncwarp();
 #pragma unroll
@@ -112,7 +117,7 @@ __device__ __forceinline__ float eval_target(const typename T::Consts& tc, const
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
       const int j = L::dim(k, lg);
-      gv[k] = (j < d) ? T::grad(tc, ctx, j, xv[k], aux[k], red) : 0.0f;
+      gv[k] = L::valid(j, d) ? T::grad(tc, ctx, j, xv[k], aux[k], red) : 0.0f;
     }
   }
   __syncwarp();  // xrow/scratch may be overwritten by the next evaluation
@@ -125,7 +130,7 @@ __device__ __forceinline__ void store_row(float* dst, const float (&xv)[L::kDPL]
 #pragma unroll
   for (int k = 0; k < DPL; k += VEC) {
     const int j = L::dim(k, lg);
-    if (j < d) {
+    if (L::valid(j, d)) {
       if (VEC == 4) {
         __stcs(reinterpret_cast<float4*>(dst + j), make_float4(xv[k], xv[k + 1], xv[k + 2], xv[k + 3]));
       } else if (VEC == 2) {
@@ -148,18 +153,25 @@ __device__ __forceinline__ void draw_normals(Key key, int d, int lg, float (&z)[
 #pragma unroll
   for (int k = 0; k < DPL; ++k) {
     float w;
-    const float u = normal_arg(bits[k], w);
+    const float u = normal_arg(bits[k], w, L::valid(L::dim(k, lg), d));
     tail |= (w >= 5.0f);
-    z[k] = (L::dim(k, lg) < d) ? 1.41421356237309515f * (erf_inv_central(w) * u) : 0.0f;
+    z[k] = 1.41421356237309515f * (erf_inv_central(w) * u);
   }
   if (tail) {  // |z| > ~2.9: 0.34 % of draws
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
       float w;
-      const float u = normal_arg(bits[k], w);
-      if (w >= 5.0f && L::dim(k, lg) < d) z[k] = 1.41421356237309515f * (erf_inv_tail(w) * u);
+      const float u = normal_arg(bits[k], w, L::valid(L::dim(k, lg), d));
+      if (w >= 5.0f) z[k] = 1.41421356237309515f * (erf_inv_tail(w) * u);
     }
   }
+}
+
+// a / b with r = __frcp_rn(b) precomputed: quotient + one residual correction (the IEEE-rounded
+// result for operands in the normal range; b is a per-launch constant here)
+__device__ __forceinline__ float div_by(float a, float b, float r) {
+  const float q = a * r;
+  return fmaf(fmaf(-q, b, a), r, q);
 }
 
 struct Slice {       // time-slicing parameters (host-computed)
@@ -197,8 +209,20 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
   const bool active = chain < a.n_chains;
   if (!active) chain = a.n_chains - 1;  // idle groups shadow the last chain; their stores are masked
   const int d = a.d;
-  float* xrow = sm.xrow[cw];
+  float* xrow = sm.xrow[cw] + kHalo;
   float* scratch = sm.scratch[cw];
+  if (lg < kHalo) {  // zero halo: targets may read x[-1] and x[d] (== 0) without bounds tests
+    xrow[-1 - lg] = 0.0f;
+    xrow[DS + lg] = 0.0f;
+  }
+  if (G < kHalo && lg == 0) {
+#pragma unroll
+    for (int q = 0; q < kHalo; ++q) {
+      xrow[-1 - q] = 0.0f;
+      xrow[DS + q] = 0.0f;
+    }
+  }
+  __syncwarp();
   const typename T::Consts tc = T::prepare(a.data, d);
 
   Key kc;
@@ -209,7 +233,7 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
       const int j = L::dim(k, lg);
-      x[k] = (j < d) ? a.x0[chain * d + j] : 0.0f;
+      x[k] = L::valid(j, d) ? a.x0[chain * d + j] : 0.0f;
       g[k] = 0.0f;
     }
     // logpdf(initial_position) seeds the scan carry (take_steps.py:177); MALA/HMC cache the gradient
@@ -238,6 +262,7 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
   const float dt2 = dt * dt;
   // scalar-covariance multivariate_normal.logpdf constant: n/2 * (log(2 pi) + log(cov))
   const float mvn_c = (float)d * 0.5f * (1.8378770664093453f + logf(dt2));
+  const float rdt2 = __frcp_rn(dt2);
 
   float cs[DPL], ld[DPL];  // HMC: column sums of the metric, diagonal of L
 #pragma unroll
@@ -246,7 +271,7 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
     ld[k] = 0.0f;
     if (KIND == KIND_HMC) {
       const int j = L::dim(k, lg);
-      if (j < d) {
+      if (L::valid(j, d)) {
         cs[k] = a.hmc_colsum[j];
         ld[k] = a.hmc_chol[(int64_t)j * d + j];
       }
@@ -257,6 +282,7 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
   const int t_last_stored = ((a.n_steps - 1) / thin) * thin;
   int o_next = (t_begin + thin - 1) / thin;  // next output index
   int t_next = o_next * thin;                // ... and the step that produces it
+  float* out_row = a.pos_buf + (chain * a.n_total + a.cursor + o_next) * d;  // advanced by d per output
 
   for (int t0 = t_begin; t0 < t_end; t0 += kChunk) {
     const int nb = min(kChunk, t_end - t0);
@@ -319,8 +345,8 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
         qb = group_sum<G>(qb);
         // MALA.py:75-81
         float ratio = lp1 - lp;
-        ratio -= (-0.5f * qa / dt2 - mvn_c);
-        ratio += (-0.5f * qb / dt2 - mvn_c);
+        ratio -= (div_by(-0.5f * qa, dt2, rdt2) - mvn_c);
+        ratio += (div_by(-0.5f * qb, dt2, rdt2) - mvn_c);
         acc = logu < ratio;
 #pragma unroll
         for (int k = 0; k < DPL; ++k) {
@@ -349,14 +375,14 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
 #pragma unroll
           for (int k = 0; k < DPL; ++k) {
             const int j = L::dim(k, lg);
-            if (j < d) scratch[j] = p[k];
+            if (L::valid(j, d)) scratch[j] = p[k];
           }
           __syncwarp();
 #pragma unroll
           for (int k = 0; k < DPL; ++k) {
             const int j = L::dim(k, lg);
             float s = 0.0f;
-            if (j < d) {
+            if (L::valid(j, d)) {
               const float* Lrow = a.hmc_chol + (int64_t)j * d;
               for (int i = 0; i <= j; ++i) s = fmaf(scratch[i], Lrow[i], s);
             }
@@ -403,7 +429,8 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
 
       // ---- outputs (take_steps.py:134-142): thinned, written in place at the cursor ----------
       if (t == t_next) {
-        if (active) store_row<L>(a.pos_buf + (chain * a.n_total + a.cursor + o_next) * d, x, d, lg);
+        if (active) store_row<L>(out_row, x, d, lg);
+        out_row += d;
         if (lg == 0) {
           sm.lpst[cw][o_next - o_first] = lp;
           sm.accst[cw][o_next - o_first] = acc ? 1.0f : 0.0f;
@@ -450,9 +477,18 @@ __global__ void __launch_bounds__(32) target_eval_kernel(const float* __restrict
                                                          int64_t n, int d, float* __restrict__ lp_out,
                                                          float* __restrict__ grad_out) {
   constexpr int G = L::kG, DPL = L::kDPL, CPW = L::CPW, DS = L::DS;
-  __shared__ __align__(16) float xrow[CPW][DS];
+  __shared__ __align__(16) float xrow_s[CPW][DS + 2 * kHalo];
   __shared__ __align__(16) float scratch[CPW][DS];
   const int lane = threadIdx.x, lg = lane % G, cw = lane / G;
+  float* xrow = xrow_s[cw] + kHalo;
+  if (lg == 0) {
+#pragma unroll
+    for (int q = 0; q < kHalo; ++q) {
+      xrow[-1 - q] = 0.0f;
+      xrow[DS + q] = 0.0f;
+    }
+  }
+  __syncwarp();
   int64_t i = (int64_t)blockIdx.x * CPW + cw;
   const bool active = i < n;
   if (!active) i = n - 1;
@@ -466,9 +502,9 @@ __global__ void __launch_bounds__(32) target_eval_kernel(const float* __restrict
   }
   float lp;
   if (grad_out != nullptr) {
-    lp = eval_target<T, L, true>(tc, x, g, xrow[cw], scratch[cw], data, d, lg);
+    lp = eval_target<T, L, true>(tc, x, g, xrow, scratch[cw], data, d, lg);
   } else {
-    lp = eval_target<T, L, false>(tc, x, g, xrow[cw], scratch[cw], data, d, lg);
+    lp = eval_target<T, L, false>(tc, x, g, xrow, scratch[cw], data, d, lg);
   }
   if (active) {
     if (lg == 0) lp_out[i] = lp;
@@ -483,17 +519,18 @@ __global__ void __launch_bounds__(32) target_eval_kernel(const float* __restrict
 }
 
 // ---- layout table and launchers --------------------------------------------------------------
-// index: 0:(1,8,1) 1:(4,8,1) 2:(8,8,1) 3:(32,16,1) | 4:(8,4,4) 5:(8,8,4) 6:(16,4,4) 7:(8,16,4)
-//        8:(16,8,4) 9:(32,4,4) 10:(16,16,4) 11:(32,8,4) 12:(32,16,4)
-constexpr int kNumLayouts = 13;
+// Scalar-store layouts (any d):   0:(1,8,1) 1:(4,8,1) 2:(8,8,1) 3:(32,4,1) 4:(32,16,1)
+// float4-store layouts (d % 4 == 0): 5:(8,4,4) 6:(16,4,4) 7:(16,8,4) 8:(32,4,4) 9:(32,8,4) 10:(32,16,4)
+// Measured on B200 (scripts/sweep_local.py): few dimensions per lane win -- more resident warps and
+// fewer registers beat the smaller key-schedule redundancy of wide lanes.
+constexpr int kNumLayouts = 11;
 
 struct LayoutInfo {
   int G, DPL, VEC;
 };
 __host__ inline LayoutInfo layout_info(int idx) {
-  static const LayoutInfo tab[kNumLayouts] = {{1, 8, 1},  {4, 8, 1},  {8, 8, 1},   {32, 16, 1}, {8, 4, 4},
-                                              {8, 8, 4},  {16, 4, 4}, {8, 16, 4},  {16, 8, 4},  {32, 4, 4},
-                                              {16, 16, 4}, {32, 8, 4}, {32, 16, 4}};
+  static const LayoutInfo tab[kNumLayouts] = {{1, 8, 1},  {4, 8, 1},  {8, 8, 1},  {32, 4, 1}, {32, 16, 1}, {8, 4, 4},
+                                              {16, 4, 4}, {16, 8, 4}, {32, 4, 4}, {32, 8, 4}, {32, 16, 4}};
   return tab[idx];
 }
 
@@ -503,17 +540,18 @@ __host__ inline int pick_layout(int d, int hint) {
     if (li.G * li.DPL >= d && (li.VEC == 1 || d % li.VEC == 0)) return hint - 1;
   }
   if (d % 4 == 0) {
-    if (d <= 32) return 4;
+    if (d <= 32) return 5;
     if (d <= 64) return 6;
-    if (d <= 128) return 8;
-    if (d <= 256) return 10;
-    if (d <= 512) return 12;
+    if (d <= 128) return 7;
+    if (d <= 256) return 9;
+    if (d <= 512) return 10;
     return -1;
   }
   if (d <= 8) return 0;
   if (d <= 32) return 1;
   if (d <= 64) return 2;
-  if (d <= 512) return 3;
+  if (d <= 128) return 3;
+  if (d <= 512) return 4;
   return -1;
 }
 
@@ -528,9 +566,9 @@ __host__ inline int64_t local_workspace_bytes(int64_t n_chains, int d, int hint)
   return head + n_groups * (2 * L.DPL + 3) * 32 * 4;
 }
 
-template <class T, int KIND, int G, int DPL, int VEC, int MINB>
+template <class T, int KIND, int G, int DPL, int VEC, int MINB, bool PAD = true>
 inline int launch_local_one(const LocalArgs* a, cudaStream_t stream) {
-  using L = Layout<G, DPL, VEC>;
+  using L = Layout<G, DPL, VEC, PAD>;
   auto kern = local_steps_kernel<T, KIND, L, MINB>;
   const int64_t n_groups = (a->n_chains + L::CPW - 1) / L::CPW;
   Slice sl{1, a->n_steps, (int)n_groups, nullptr, nullptr, nullptr};
@@ -584,6 +622,13 @@ inline int launch_local_one(const LocalArgs* a, cudaStream_t stream) {
   return 0;
 }
 
+// float4 layouts come in two flavours: exact (d == G*DPL, no padding tests) and padded
+template <class T, int KIND, int G, int DPL, int MINB>
+inline int launch_local_v4(const LocalArgs* a, cudaStream_t stream) {
+  if (a->d == G * DPL) return launch_local_one<T, KIND, G, DPL, 4, MINB, false>(a, stream);
+  return launch_local_one<T, KIND, G, DPL, 4, MINB, true>(a, stream);
+}
+
 template <class T, int KIND>
 inline int launch_local_kind(const LocalArgs* a, cudaStream_t stream) {
   const int li = pick_layout(a->d, a->layout_hint);
@@ -591,16 +636,14 @@ inline int launch_local_kind(const LocalArgs* a, cudaStream_t stream) {
     case 0: return launch_local_one<T, KIND, 1, 8, 1, 16>(a, stream);
     case 1: return launch_local_one<T, KIND, 4, 8, 1, 16>(a, stream);
     case 2: return launch_local_one<T, KIND, 8, 8, 1, 16>(a, stream);
-    case 3: return launch_local_one<T, KIND, 32, 16, 1, 12>(a, stream);
-    case 4: return launch_local_one<T, KIND, 8, 4, 4, 24>(a, stream);
-    case 5: return launch_local_one<T, KIND, 8, 8, 4, 16>(a, stream);
-    case 6: return launch_local_one<T, KIND, 16, 4, 4, 24>(a, stream);
-    case 7: return launch_local_one<T, KIND, 8, 16, 4, 12>(a, stream);
-    case 8: return launch_local_one<T, KIND, 16, 8, 4, 16>(a, stream);
-    case 9: return launch_local_one<T, KIND, 32, 4, 4, 24>(a, stream);
-    case 10: return launch_local_one<T, KIND, 16, 16, 4, 12>(a, stream);
-    case 11: return launch_local_one<T, KIND, 32, 8, 4, 16>(a, stream);
-    case 12: return launch_local_one<T, KIND, 32, 16, 4, 12>(a, stream);
+    case 3: return launch_local_one<T, KIND, 32, 4, 1, 24>(a, stream);
+    case 4: return launch_local_one<T, KIND, 32, 16, 1, 12>(a, stream);
+    case 5: return launch_local_v4<T, KIND, 8, 4, 24>(a, stream);
+    case 6: return launch_local_v4<T, KIND, 16, 4, 24>(a, stream);
+    case 7: return launch_local_v4<T, KIND, 16, 8, 16>(a, stream);
+    case 8: return launch_local_v4<T, KIND, 32, 4, 24>(a, stream);
+    case 9: return launch_local_v4<T, KIND, 32, 8, 16>(a, stream);
+    case 10: return launch_local_v4<T, KIND, 32, 16, 12>(a, stream);
     default:
       flowmc_set_error("local_steps: unsupported dimension (d must be <= 512)");
       return -2;

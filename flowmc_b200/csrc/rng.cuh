@@ -79,11 +79,18 @@ __device__ __forceinline__ float bits_to_uniform01(uint32_t bits) { return fmaxf
 // the polynomials only through (w - 2.5) / (sqrt(w) - 3), so the result agrees with the oracle's
 // libm evaluation to ~1e-6 relative (tests/test_gpu_rng.py).  The three pieces are separate so
 // that callers can run the branch-free central polynomial on every draw and patch the rare tail.
-__device__ __forceinline__ float normal_arg(uint32_t bits, float& w) {
+__device__ __forceinline__ float lg2_ftz(float x) {  // one MUFU.LG2; the argument is never denormal here
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// `valid == false` (a padding dimension) forces u = 0, hence w = 0 and a draw of exactly 0.
+__device__ __forceinline__ float normal_arg(uint32_t bits, float& w, bool valid = true) {
   const float lo = -0.99999994f;  // nextafter(-1, 0): jax.random.normal's uniform minval
-  const float u = fmaxf(lo, fmaf(bits_to_unit(bits), 2.0f, lo));
+  float u = fmaxf(lo, fmaf(bits_to_unit(bits), 2.0f, lo));
+  u = valid ? u : 0.0f;
   const float xx = __fmul_rn(u, u);
-  w = -0.6931471805599453f * __log2f(1.0f - xx);
+  w = -0.6931471805599453f * lg2_ftz(1.0f - xx);
   return u;
 }
 __device__ __forceinline__ float erf_inv_central(float w) {

@@ -8,18 +8,15 @@ struct Rosenbrock {
   struct Consts {};
   __device__ static Consts prepare(const float* data, int d) { return Consts{}; }
   __device__ static float partial(const Consts& k, const flowmc::TargetCtx& c, int j, float xj, float* red) {
-    float gj = 0.0f;
-    if (j < c.d - 1) {
-      const float u = c.x[j + 1] - xj * xj;
-      const float v = 1.0f - xj;
-      red[0] += (100.0f * u * u + v * v) / 20.0f;
-      gj += (400.0f * xj * u + 2.0f * v) / 20.0f;
-    }
-    if (j > 0) {
-      const float xm = c.x[j - 1];
-      const float um = xj - xm * xm;
-      gj += (-200.0f * um) / 20.0f;
-    }
+    // branch-free: x[-1] and x[d] are readable (zero halo); boundary terms are masked by selects
+    const float u = c.x[j + 1] - xj * xj;
+    const float v = 1.0f - xj;
+    const bool has_next = j < c.d - 1;
+    red[0] += has_next ? (100.0f * u * u + v * v) / 20.0f : 0.0f;
+    float gj = has_next ? (400.0f * xj * u + 2.0f * v) / 20.0f : 0.0f;
+    const float xm = c.x[j - 1];
+    const float um = xj - xm * xm;
+    gj += (j > 0) ? (-200.0f * um) / 20.0f : 0.0f;
     return gj;
   }
   __device__ static float finish(const Consts& k, const flowmc::TargetCtx& c, float* red) { return -red[0]; }

@@ -13,15 +13,17 @@
 // (each lane owns a few dimensions, held in registers) and mirrored in a shared-memory row that
 // the target may read freely.  One evaluation is three calls:
 //
-//   aux_j = T::partial(ctx, j, x_j, red)   for every owned dimension j: add this dimension's
+//   k     = T::prepare(data, d)            once per kernel: a small struct of constants (registers)
+//   aux_j = T::partial(k, ctx, j, x_j, red)   for every owned dimension j: add this dimension's
 //                                          contribution(s) to red[0..NRED); return any per-
 //                                          dimension value grad() will want (e.g. (P x)_j)
 //   -- the kernel sums red[] over the chain's lanes --
-//   logp  = T::finish(ctx, red)            every lane of the group: turn the reduced scalars into
+//   logp  = T::finish(k, ctx, red)            every lane of the group: turn the reduced scalars into
 //                                          log p(x); may overwrite red[] with whatever grad() needs
-//   g_j   = T::grad(ctx, j, x_j, aux_j, red)  for every owned dimension j: d log p / d x_j
+//   g_j   = T::grad(k, ctx, j, x_j, aux_j, red)  for every owned dimension j: d log p / d x_j
 //
-// `ctx.x` is the full vector (read-only), `ctx.data` the packed float32 parameter block built on
+// `ctx.x` is the full vector (read-only; x[-1] and x[d] are readable and hold 0, so nearest-
+// neighbour couplings need no bounds tests), `ctx.data` the packed float32 parameter block built on
 // the host (the reference's `data` pytree; layout is target-defined), `ctx.scratch` a private
 // row of >= d floats in shared memory (valid only if USES_SCRATCH).  partial() of all owned
 // dimensions completes (with a warp barrier) before finish()/grad() run.

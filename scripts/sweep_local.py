@@ -11,8 +11,8 @@ sys.path.insert(0, "/root/repo")
 from flowmc_b200 import random as frandom, targets as T
 from flowmc_b200._lib import LocalParams, check, lib
 
-LAYOUTS = [(1, 8, 1), (4, 8, 1), (8, 8, 1), (32, 16, 1), (8, 4, 4), (8, 8, 4), (16, 4, 4), (8, 16, 4),
-           (16, 8, 4), (32, 4, 4), (16, 16, 4), (32, 8, 4), (32, 16, 4)]
+LAYOUTS = [(1, 8, 1), (4, 8, 1), (8, 8, 1), (32, 4, 1), (32, 16, 1), (8, 4, 4), (16, 4, 4), (16, 8, 4),
+           (32, 4, 4), (32, 8, 4), (32, 16, 4)]
 u32p = C.POINTER(C.c_uint32)
 
 
@@ -67,7 +67,7 @@ if __name__ == "__main__":
         for h, (G, DPL, VEC) in enumerate(LAYOUTS, 1):
             if G * DPL < d or (VEC == 4 and d % 4) or G * DPL > 4 * d:
                 continue
-            for use_ws in (False, True):
+            for use_ws in (True,):
                 try:
                     ms, rate, acc = run(kind, tgt, d, n, steps, h, ss, nl, use_ws=use_ws)
                     bytes_per = 4 * (d + 2)

@@ -136,15 +136,16 @@ def test_take_serial_steps_parity(cuda, cfg):
     assert set(np.unique(ga)) <= {0.0, 1.0}
 
 
-@pytest.mark.parametrize("hint", list(range(1, 14)))
+@pytest.mark.parametrize("hint", list(range(1, 12)))
 def test_every_layout_gives_the_same_chains(cuda, hint):
     """All lane layouts of the persistent kernel are the same algorithm: identical flags."""
     from flowmc_b200 import random as frandom
     from flowmc_b200.resource.kernel.MALA import MALA
     from oracle import local as olocal
-    G, DPL, VEC = [(1, 8, 1), (4, 8, 1), (8, 8, 1), (32, 16, 1), (8, 4, 4), (8, 8, 4), (16, 4, 4), (8, 16, 4),
-                   (16, 8, 4), (32, 4, 4), (16, 16, 4), (32, 8, 4), (32, 16, 4)][hint - 1]
-    d = G * DPL if VEC == 4 else max(1, G * DPL - 3)
+    G, DPL, VEC = [(1, 8, 1), (4, 8, 1), (8, 8, 1), (32, 4, 1), (32, 16, 1), (8, 4, 4), (16, 4, 4), (16, 8, 4),
+                   (32, 4, 4), (32, 8, 4), (32, 16, 4)][hint - 1]
+    # float4 layouts: even hints run the exact variant (d == G*DPL), odd ones the padded variant
+    d = (G * DPL if hint % 2 == 0 else G * DPL - 4) if VEC == 4 else max(2, G * DPL - 3)
     n, T_ = 19, 37
     tgt, data, packed = _make("ar1_gaussian", d)
     key = frandom.PRNGKey(hint)
