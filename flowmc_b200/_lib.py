@@ -30,6 +30,29 @@ class LocalParams(C.Structure):
     ]
 
 
+class FlowDesc(C.Structure):
+    _fields_ = [
+        ("n_features", C.c_int), ("n_layers", C.c_int), ("n_linear", C.c_int), ("num_bins", C.c_int),
+        ("dims", C.c_int * 5),
+        ("range_min", C.c_float), ("range_max", C.c_float),
+        ("off_W", C.c_int64 * 4), ("off_b", C.c_int64 * 4), ("off_scale", C.c_int64), ("off_shift", C.c_int64),
+        ("layer_stride", C.c_int64),
+        ("off_data_mean", C.c_int64), ("off_data_cov", C.c_int64), ("off_base_mean", C.c_int64),
+        ("off_base_cov", C.c_int64),
+        ("n_params", C.c_int64),
+    ]
+
+
+class GlobalParams(C.Structure):
+    _fields_ = [
+        ("n_batch_size", C.c_int),
+        ("chain_keys", C.c_void_p),
+        ("lp0", C.c_void_p),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_int64),
+    ]
+
+
 def _load() -> C.CDLL:
     if not _LIB_PATH.exists():
         raise ImportError(
@@ -54,6 +77,23 @@ def _load() -> C.CDLL:
                                      C.POINTER(LocalParams), u32p, vp, vp]),
         "flowmc_launch_count": (i64, []),
         "flowmc_local_steps_workspace_bytes": (i64, [i64, i32, i32]),
+        "flowmc_flow_desc_init": (i32, [C.POINTER(FlowDesc), i32, i32, i32, C.POINTER(C.c_int), i32, f32, f32]),
+        "flowmc_flow_forward": (i32, [C.POINTER(FlowDesc), vp, vp, i64, vp, vp, vp]),
+        "flowmc_flow_inverse": (i32, [C.POINTER(FlowDesc), vp, vp, i64, vp, vp, vp]),
+        "flowmc_flow_log_prob": (i32, [C.POINTER(FlowDesc), vp, vp, i64, vp, vp, vp]),
+        "flowmc_flow_sample": (i32, [C.POINTER(FlowDesc), vp, vp, u32p, i64, i64, vp, vp]),
+        "flowmc_flow_loss_grad_workspace_bytes": (i64, [C.POINTER(FlowDesc), i64]),
+        "flowmc_flow_loss_grad": (i32, [C.POINTER(FlowDesc), vp, vp, vp, i64, f32, vp, vp, vp, i64, vp]),
+        "flowmc_clip_adamw": (i32, [i64, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp, vp, vp]),
+        "flowmc_random_permutation_workspace_bytes": (i64, [i64]),
+        "flowmc_random_permutation": (i32, [u32p, i64, vp, vp, i64, vp]),
+        "flowmc_random_choice": (i32, [u32p, i64, i64, vp, vp]),
+        "flowmc_buffer_finite_rows": (i32, [vp, i64, i64, i32, vp, vp, vp, vp]),
+        "flowmc_gather_training_rows": (i32, [vp, vp, i64, i32, i32, i32, i64, i64, vp, i64, vp, vp]),
+        "flowmc_data_mean_cov": (i32, [vp, i64, i32, vp, vp, vp, vp]),
+        "flowmc_nf_global_steps_workspace_bytes": (i64, [i64, i32, i32]),
+        "flowmc_nf_global_steps": (i32, [C.POINTER(FlowDesc), vp, i32, vp, u32p, vp, vp, vp, vp, i64, i64, i64, i32,
+                                         i32, i64, i64, C.POINTER(GlobalParams), u32p, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -40,7 +40,10 @@ def _compile(src: Path, hdr_m: float, verbose: bool) -> tuple[Path, str]:
     obj.parent.mkdir(parents=True, exist_ok=True)
     log = ""
     if (not obj.exists()) or obj.stat().st_mtime < max(src.stat().st_mtime, hdr_m):
-        cmd = [NVCC, *ARCH, *CFLAGS, "-c", str(src), "-o", str(obj)]
+        # flow kernels: no implicit FMA contraction, so the spline arithmetic rounds like the reference's
+        # op-by-op float32 evaluation (explicit fmaf() in the GEMM loops is unaffected)
+        extra = ["-fmad=false"] if src.name.startswith(("flow", "nf_")) else []
+        cmd = [NVCC, *ARCH, *CFLAGS, *extra, "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         if r.returncode != 0:

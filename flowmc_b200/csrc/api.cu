@@ -106,7 +106,7 @@ const char* flowmc_target_name(int id) {
   return r.targets[id].name;
 }
 
-static int get_target(int id, FlowmcTargetVTable* out) {
+int flowmc_get_target(int id, FlowmcTargetVTable* out) {
   Registry& r = registry();
   std::lock_guard<std::mutex> lk(r.mu);
   if (id < 0 || id >= (int)r.targets.size()) return fail(FLOWMC_ERR_NOT_FOUND, "invalid target id");
@@ -117,7 +117,7 @@ static int get_target(int id, FlowmcTargetVTable* out) {
 int flowmc_target_eval(int target_id, const float* data, const float* x, int64_t n, int d, float* logp_out,
                        float* grad_out, void* stream) {
   FlowmcTargetVTable vt;
-  if (int rc = get_target(target_id, &vt)) return rc;
+  if (int rc = flowmc_get_target(target_id, &vt)) return rc;
   if (n < 0 || d <= 0 || !x || !logp_out) return fail(FLOWMC_ERR_INVALID, "target_eval: bad arguments");
   if (n == 0) return FLOWMC_OK;
   return vt.eval(data, x, n, d, logp_out, grad_out, (cudaStream_t)stream);
@@ -170,7 +170,7 @@ int flowmc_local_steps(int kind, int target_id, const float* target_data, const 
                        int64_t n_chains_global, const FlowmcLocalParams* params, uint32_t key_out[2],
                        float* last_pos, void* stream) {
   FlowmcTargetVTable vt;
-  if (int rc = get_target(target_id, &vt)) return rc;
+  if (int rc = flowmc_get_target(target_id, &vt)) return rc;
   if (!key || !params || !key_out) return fail(FLOWMC_ERR_INVALID, "local_steps: null key/params");
   if (n_chains < 0 || d <= 0 || n_steps < 0 || thinning <= 0)
     return fail(FLOWMC_ERR_INVALID, "local_steps: bad sizes");

@@ -51,4 +51,6 @@ typedef struct FlowmcTargetVTable {
 __attribute__((visibility("default"))) int flowmc_register_target(const FlowmcTargetVTable* vt);
 __attribute__((visibility("default"))) void flowmc_set_error(const char* msg);
 __attribute__((visibility("default"))) void flowmc_count_launch(void);
+// copies the vtable of a registered target (0, or FLOWMC_ERR_NOT_FOUND with the error message set)
+__attribute__((visibility("default"))) int flowmc_get_target(int target_id, FlowmcTargetVTable* out);
 }

@@ -114,6 +114,110 @@ FLOWMC_API int flowmc_local_steps(int kind, int target_id, const float* target_d
                        int64_t chain_offset, int64_t n_chains_global, const FlowmcLocalParams* params,
                        uint32_t key_out[2], float* last_pos, void* stream);
 
+/* ---- MaskedCouplingRQSpline flow (resource/model/nf_model/rqSpline.py:392-504) ---------------
+ * The model is ONE flat float32 parameter blob on the device (so that the optimiser and the
+ * gradient all-reduce see a single vector) described by FlowmcFlowDesc.  Offsets are in floats;
+ * every array starts on a 4-float boundary (padding is zero and stays zero under AdamW).
+ *   per layer l at l*layer_stride:  for i in 0..n_linear-1: W_i [out_i, in_i] row-major (equinox
+ *     nn.Linear layout, common.py:95-101), b_i [out_i];  then scale, shift (ScalarAffine, trainable)
+ *   tail: data_mean [d], data_cov [d,d], base mean [d], base cov [d,d]
+ * Linear i maps dims[i] -> dims[i+1] with dims = [d, hidden..., d*(3*num_bins+1)].
+ * Layer l transforms the features f with (f + l) % 2 == 0 (mask False, rqSpline.py:434). */
+#define FLOWMC_FLOW_MAX_LINEAR 4
+typedef struct FlowmcFlowDesc {
+  int n_features, n_layers, n_linear, num_bins;
+  int dims[FLOWMC_FLOW_MAX_LINEAR + 1];
+  float range_min, range_max;
+  int64_t off_W[FLOWMC_FLOW_MAX_LINEAR], off_b[FLOWMC_FLOW_MAX_LINEAR], off_scale, off_shift;
+  int64_t layer_stride;
+  int64_t off_data_mean, off_data_cov, off_base_mean, off_base_cov;
+  int64_t n_params; /* total floats in the blob */
+} FlowmcFlowDesc;
+
+/* fills `desc` for (n_features, n_layers, hidden[n_hidden], num_bins, spline range) */
+FLOWMC_API int flowmc_flow_desc_init(FlowmcFlowDesc* desc, int n_features, int n_layers, int n_hidden,
+                                     const int* hidden, int num_bins, float range_min, float range_max);
+
+/* forward / inverse of the bijection on n rows: x device [n,d] -> y device [n,d], logdet device [n]
+ * (MaskedCouplingRQSpline.forward / .inverse, rqSpline.py:450-488; no whitening) */
+FLOWMC_API int flowmc_flow_forward(const FlowmcFlowDesc* desc, const float* params, const float* x, int64_t n,
+                                   float* y, float* logdet, void* stream);
+FLOWMC_API int flowmc_flow_inverse(const FlowmcFlowDesc* desc, const float* params, const float* x, int64_t n,
+                                   float* y, float* logdet, void* stream);
+/* log_prob(x) = logdet(forward((x - data_mean)/sqrt(diag data_cov))) + base.log_prob  (rqSpline.py:498-504);
+ * layer_inputs (optional, device [n_layers + 1, n, d]) receives each layer's input and, in the last slot,
+ * the final latent (what the training backward pass starts from) */
+FLOWMC_API int flowmc_flow_log_prob(const FlowmcFlowDesc* desc, const float* params, const float* x, int64_t n,
+                                    float* log_prob, float* layer_inputs, void* stream);
+/* sample: row r draws z = normal(key_k, (rows_per_key, d))[r % rows_per_key] with k = r / rows_per_key, then
+ * x = inverse(base_mean + sqrt(diag base_cov) z) * sqrt(diag data_cov) + data_mean  (rqSpline.py:490-496).
+ * keys: device uint32 [ceil(n / rows_per_key), 2], or NULL to use the single host key `host_key`. */
+FLOWMC_API int flowmc_flow_sample(const FlowmcFlowDesc* desc, const float* params, const uint32_t* keys,
+                                  const uint32_t host_key[2], int64_t rows_per_key, int64_t n, float* x_out,
+                                  void* stream);
+
+/* ---- NFProposal global steps (strategy/take_steps.py:191-206 + resource/kernel/NF_proposal.py:27-172) ---- */
+typedef struct FlowmcGlobalParams {
+  int n_batch_size;           /* NFProposal.n_batch_size: only changes the proposals' key schedule */
+  const uint32_t* chain_keys; /* optional, device [n_chains,2]: explicit per-chain rng_key (NFProposal.kernel
+                               * called directly); NULL = split(subkey, n_chains_global)[global chain index] */
+  const float* lp0;           /* optional, device [n_chains]: incoming log_prob; NULL = logpdf(x0) (take_steps.py:201) */
+  void* workspace;            /* device scratch: proposals and their log-probs; size from
+                               * flowmc_nf_global_steps_workspace_bytes() */
+  int64_t workspace_bytes;
+} FlowmcGlobalParams;
+
+FLOWMC_API int64_t flowmc_nf_global_steps_workspace_bytes(int64_t n_chains, int d, int n_steps);
+
+/* n_steps independence-MH steps with flow proposals for n_chains chains; buffers, cursor, thinning, key,
+ * key_out, last_pos and chain sharding exactly as flowmc_local_steps.  Proposals, their flow log-probs
+ * (a forward pass, as the reference does), the target log-probs and the sequential accept scan all run on
+ * the device; nothing is read back. */
+FLOWMC_API int flowmc_nf_global_steps(const FlowmcFlowDesc* desc, const float* params, int target_id,
+                                      const float* target_data, const uint32_t key[2], const float* x0,
+                                      float* pos_buf, float* lp_buf, float* acc_buf, int64_t n_total, int64_t cursor,
+                                      int64_t n_chains, int n_steps, int thinning, int64_t chain_offset,
+                                      int64_t n_chains_global, const FlowmcGlobalParams* params_g,
+                                      uint32_t key_out[2], float* last_pos, void* stream);
+
+/* ---- flow training (resource/model/nf_model/base.py:98-210, resource/optimizer.py:19-23) ------------------ */
+FLOWMC_API int64_t flowmc_flow_loss_grad_workspace_bytes(const FlowmcFlowDesc* desc, int64_t n);
+/* NFModel.loss_fn + its gradient (base.py:98-100,122) for the rows x[idx[0..n)] (idx NULL = rows 0..n):
+ *   loss[0]  = -sum_i log_prob(x_i) * inv_n_total,   grad[0..n_params) = d loss / d params
+ * (both device, OVERWRITTEN).  inv_n_total = 1 / (global batch size): data-parallel ranks each pass their slice
+ * of the batch and sum-all-reduce grad and loss.  The non-trainable tail (data_mean, data_cov, base mean/cov)
+ * gets zero gradient, as under the reference's stop_gradient. */
+FLOWMC_API int flowmc_flow_loss_grad(const FlowmcFlowDesc* desc, const float* params, const float* x,
+                                     const int32_t* idx, int64_t n, float inv_n_total, float* grad, float* loss,
+                                     void* workspace, int64_t workspace_bytes, void* stream);
+/* optax.chain(clip_by_global_norm(max_norm), adamw(lr, b1, b2, eps, weight_decay)) applied in place to the flat
+ * vectors (all device, n_params floats): params, Adam moments mu / nu.  count = 1-based step number (optax's
+ * count after increment); scratch: device, >= 256 floats; gnorm_out: optional device float (pre-clip norm). */
+FLOWMC_API int flowmc_clip_adamw(int64_t n_params, float* params, const float* grads, float* mu, float* nu,
+                                 int64_t count, float lr, float b1, float b2, float eps, float weight_decay,
+                                 float max_norm, float* scratch, float* gnorm_out, void* stream);
+
+/* ---- training-set plumbing (strategy/train_model.py:66-81, nf_model/base.py:141-144,187-188) --------------- */
+/* jax.random.permutation(key, n) -> out device int32[n] */
+FLOWMC_API int64_t flowmc_random_permutation_workspace_bytes(int64_t n);
+FLOWMC_API int flowmc_random_permutation(const uint32_t key[2], int64_t n, int32_t* out, void* workspace,
+                                         int64_t workspace_bytes, void* stream);
+/* jax.random.choice(key, arange(n_population), (m,), replace=True) -> out device int32[m] */
+FLOWMC_API int flowmc_random_choice(const uint32_t key[2], int64_t n_population, int64_t m, int32_t* out,
+                                    void* stream);
+/* per chain of buf [n_chains, n_total, d]: rowmap[c][k] = step of the k-th finite row, counts[c] = number of
+ * finite rows, minmax = {min, max} over chains of counts (all device int32) */
+FLOWMC_API int flowmc_buffer_finite_rows(const float* buf, int64_t n_chains, int64_t n_total, int d, int32_t* rowmap,
+                                         int32_t* counts, int32_t* minmax, void* stream);
+/* out[i] = row idx[i] of the population "last `window` of each chain's m_finite finite rows" (row q belongs to
+ * global chain q / window); only rows of chains in [chain_lo, chain_hi) (this rank's slab buf) are written */
+FLOWMC_API int flowmc_gather_training_rows(const float* buf, const int32_t* rowmap, int64_t n_total, int d,
+                                           int window, int m_finite, int64_t chain_lo, int64_t chain_hi,
+                                           const int32_t* idx, int64_t m, float* out, void* stream);
+/* jnp.mean(x, 0) and jnp.cov(x.T) of x device [n, d]; scratch: device, >= d floats */
+FLOWMC_API int flowmc_data_mean_cov(const float* x, int64_t n, int d, float* mean, float* cov, float* scratch,
+                                    void* stream);
+
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 FLOWMC_API int64_t flowmc_launch_count(void);
 
