@@ -60,7 +60,7 @@ def _load() -> C.CDLL:
             "Run `python -m flowmc_b200.build` (needs nvcc); there is no CPU fallback."
         )
     lib = C.CDLL(str(_LIB_PATH), mode=C.RTLD_GLOBAL)
-    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
     u32p = C.POINTER(C.c_uint32)
     sigs = {
         "flowmc_abi_version": (i32, []),
@@ -84,7 +84,7 @@ def _load() -> C.CDLL:
         "flowmc_flow_sample": (i32, [C.POINTER(FlowDesc), vp, vp, u32p, i64, i64, vp, vp]),
         "flowmc_flow_loss_grad_workspace_bytes": (i64, [C.POINTER(FlowDesc), i64]),
         "flowmc_flow_loss_grad": (i32, [C.POINTER(FlowDesc), vp, vp, vp, i64, f32, vp, vp, vp, i64, vp]),
-        "flowmc_clip_adamw": (i32, [i64, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp, vp, vp]),
+        "flowmc_clip_adamw": (i32, [i64, vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, f64, vp, vp, vp]),
         "flowmc_random_permutation_workspace_bytes": (i64, [i64]),
         "flowmc_random_permutation": (i32, [u32p, i64, vp, vp, i64, vp]),
         "flowmc_random_choice": (i32, [u32p, i64, i64, vp, vp]),

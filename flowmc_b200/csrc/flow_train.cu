@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
 }
 
 struct AdamArgs {
-  float lr, b1, b2, eps, wd, max_norm, bc1, bc2;  // bc = 1 - b^count
+  float lr, b1, b2, omb1, omb2, eps, wd, max_norm, bc1, bc2;  // omb = 1 - b (rounded from double), bc = 1 - b^count
 };
 
 __global__ void __launch_bounds__(256) clip_adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -629,8 +629,8 @@ __global__ void __launch_bounds__(256) clip_adamw_kernel(float* __restrict__ p, 
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     float gi = g[i];
     if (!keep) gi = (gi / gn) * a.max_norm;
-    const float m = (1.0f - a.b1) * gi + a.b1 * mu[i];          // optax.scale_by_adam
-    const float v = (1.0f - a.b2) * (gi * gi) + a.b2 * nu[i];
+    const float m = a.omb1 * gi + a.b1 * mu[i];                  // optax.scale_by_adam / update_moment
+    const float v = a.omb2 * (gi * gi) + a.b2 * nu[i];
     mu[i] = m;
     nu[i] = v;
     float u = (m / a.bc1) / (sqrtf(v / a.bc2) + a.eps);
@@ -682,8 +682,8 @@ int flowmc_flow_loss_grad(const FlowmcFlowDesc* D, const float* params, const fl
 }
 
 int flowmc_clip_adamw(int64_t n_params, float* params, const float* grads, float* mu, float* nu, int64_t count,
-                      float lr, float b1, float b2, float eps, float weight_decay, float max_norm, float* scratch,
-                      float* gnorm_out, void* stream_) {
+                      double lr, double b1, double b2, double eps, double weight_decay, double max_norm,
+                      float* scratch, float* gnorm_out, void* stream_) {
   using namespace flowmc;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_params < 0 || count < 1 || (n_params > 0 && (!params || !grads || !mu || !nu || !scratch))) {
@@ -694,9 +694,14 @@ int flowmc_clip_adamw(int64_t n_params, float* params, const float* grads, float
   sumsq_partial_kernel<<<kNormBlocks, 256, 0, stream>>>(grads, n_params, scratch);
   flowmc_count_launch();
   AdamArgs a;
-  a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.wd = weight_decay; a.max_norm = max_norm;
-  a.bc1 = 1.0f - powf(b1, (float)count);
-  a.bc2 = 1.0f - powf(b2, (float)count);
+  // optax works with Python-float hyperparameters: (1 - decay) is formed in double and only then rounded to
+  // float32 by the multiply; decay ** count is a float32 power of the float32-rounded decay
+  a.lr = (float)lr; a.b1 = (float)b1; a.b2 = (float)b2; a.eps = (float)eps; a.wd = (float)weight_decay;
+  a.max_norm = (float)max_norm;
+  a.omb1 = (float)(1.0 - b1);
+  a.omb2 = (float)(1.0 - b2);
+  a.bc1 = 1.0f - powf(a.b1, (float)count);
+  a.bc2 = 1.0f - powf(a.b2, (float)count);
   int64_t blocks = (n_params + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   clip_adamw_kernel<<<(unsigned)blocks, 256, 0, stream>>>(params, grads, mu, nu, n_params, scratch, a, gnorm_out);

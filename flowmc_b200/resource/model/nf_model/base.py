@@ -11,9 +11,37 @@ clip-by-global-norm + AdamW update (``flowmc_clip_adamw``).  The host reads ONE 
 """
 from __future__ import annotations
 
+import ctypes as C
 from abc import abstractmethod
 
+import numpy as np
+import torch
+
+from .... import random as frandom
+from ...._lib import check, lib
 from ...base import Resource
+
+_u32p = C.POINTER(C.c_uint32)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _TrainScratch:
+    """Device scratch of one ``train`` call (allocated once, reused by every step)."""
+
+    def __init__(self, model, n_rows: int, batch_rows: int):
+        dev = model.params.device
+        d = model.desc
+        self.grad = torch.empty(int(d.n_params), dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.ws = torch.empty(max(16, int(lib.flowmc_flow_loss_grad_workspace_bytes(C.byref(d), batch_rows))),
+                              dtype=torch.uint8, device=dev)
+        self.perm = torch.empty(max(1, n_rows), dtype=torch.int32, device=dev)
+        self.perm_ws = torch.empty(max(16, int(lib.flowmc_random_permutation_workspace_bytes(n_rows))),
+                                   dtype=torch.uint8, device=dev)
+        self.small = torch.empty(1024, dtype=torch.float32, device=dev)
 
 
 class NFModel(Resource):
@@ -45,6 +73,108 @@ class NFModel(Resource):
     @abstractmethod
     def inverse(self, x):
         raise NotImplementedError
+
+    # ---- training (nf_model/base.py:98-210) -----------------------------------------------------
+    # Data parallelism: ``dp = (rank, world_size, all_reduce)`` -- every rank holds the full training set
+    # and the identical permutation, takes its contiguous slice of each global batch, and the flat
+    # gradient + loss are sum-all-reduced before the (identical) optimiser step on every rank.
+    dp = None
+
+    def loss_and_grad(self, x, idx=None, scratch=None, n_global=None):
+        """NFModel.loss_fn (base.py:98-100): (-mean log_prob, flat gradient).  ``idx`` (int32 device
+        tensor) selects rows of ``x``."""
+        x = x.contiguous()
+        n = int(idx.numel()) if idx is not None else int(x.shape[0])
+        sc = scratch or _TrainScratch(self, 0, n)
+        with torch.cuda.device(x.device):
+            check(lib.flowmc_flow_loss_grad(C.byref(self.desc), self.params.data_ptr(), x.data_ptr(),
+                                            idx.data_ptr() if idx is not None else None, n,
+                                            1.0 / float(n_global or n), sc.grad.data_ptr(), sc.loss.data_ptr(),
+                                            sc.ws.data_ptr(), sc.ws.numel(), _stream()))
+        return sc.loss, sc.grad
+
+    def _apply_update(self, optim, state, sc):
+        state.count += 1
+        check(lib.flowmc_clip_adamw(self.params.numel(), self.params.data_ptr(), sc.grad.data_ptr(),
+                                    state.mu.data_ptr(), state.nu.data_ptr(), state.count,
+                                    optim.learning_rate, optim.b1, optim.b2, optim.eps, optim.weight_decay,
+                                    optim.max_norm, sc.small.data_ptr(), None, _stream()))
+
+    def train_step(self, x, optim, state, idx=None, scratch=None):
+        """One optimisation step IN PLACE on this model and ``state`` (base.py:102-125); returns the
+        loss as a 1-element device tensor (no host synchronisation)."""
+        n = int(idx.numel()) if idx is not None else int(x.shape[0])
+        sc = scratch or _TrainScratch(self, 0, n)
+        if self.dp is None:
+            self.loss_and_grad(x, idx, sc)
+        else:
+            rank, world, all_reduce = self.dp
+            per = -(-n // world)
+            lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+            if idx is None:
+                self.loss_and_grad(x[lo:hi], None, sc, n_global=n)
+            else:
+                self.loss_and_grad(x, idx[lo:hi], sc, n_global=n)
+            all_reduce(sc.grad)
+            all_reduce(sc.loss)
+        self._apply_update(optim, state, sc)
+        return sc.loss
+
+    def train_epoch(self, rng, optim, state, data, batch_size, scratch=None):
+        """base.py:127-151: permutation batches (incomplete tail skipped), in place; returns the last
+        batch's loss (device tensor)."""
+        n = int(data.shape[0])
+        steps = n // int(batch_size)
+        sc = scratch or _TrainScratch(self, n, int(batch_size) if steps > 0 else n)
+        value = None
+        if steps > 0:
+            key = np.ascontiguousarray(rng, dtype=np.uint32)
+            with torch.cuda.device(data.device):
+                check(lib.flowmc_random_permutation(key.ctypes.data_as(_u32p), n, sc.perm.data_ptr(),
+                                                    sc.perm_ws.data_ptr(), sc.perm_ws.numel(), _stream()))
+            for b in range(steps):
+                value = self.train_step(data, optim, state, sc.perm[b * batch_size:(b + 1) * batch_size], sc)
+        else:
+            value = self.train_step(data, optim, state, None, sc)
+        return value
+
+    def train(self, rng, data, optim, state, num_epochs: int, batch_size: int, verbose: bool = True):
+        """base.py:153-210.  Functional like the reference: ``self`` and ``state`` are left untouched;
+        returns ``(rng, best_model, best_state, loss_values)`` where best = lowest last-batch loss."""
+        data = torch.as_tensor(data, dtype=torch.float32)
+        if not data.is_cuda:
+            data = data.to(self.params.device)
+        data = data.contiguous()
+        n, d = data.shape
+        batch_size = int(batch_size)
+        steps = n // batch_size
+        model = self.clone()
+        model.dp = self.dp
+        state = state.clone()
+        best_model, best_state, best_loss = self, state.clone(), 1e9
+        sc = _TrainScratch(model, n, batch_size if steps > 0 else n)
+        with torch.cuda.device(data.device):                      # base.py:187-188
+            check(lib.flowmc_data_mean_cov(data.data_ptr(), n, d, model.data_mean.data_ptr(),
+                                           model.data_cov.data_ptr(), sc.small.data_ptr(), _stream()))
+        loss_values = np.zeros(num_epochs, np.float32)
+        rng = np.asarray(rng, dtype=np.uint32)
+        it = range(num_epochs)
+        if verbose:
+            from tqdm import trange
+            it = trange(num_epochs, desc="Training NF", miniters=max(1, int(num_epochs / 10)))
+        for epoch in it:
+            rng, input_rng = frandom.split(rng)
+            value = model.train_epoch(input_rng, optim, state, data, batch_size, sc)
+            loss_values[epoch] = float(value.item())              # the reference's per-epoch host read
+            if loss_values[epoch] < best_loss:
+                if best_model is self:
+                    best_model = model.clone()
+                else:
+                    best_model.params.copy_(model.params)
+                best_state.copy_(state)
+                best_loss = loss_values[epoch]
+        best_model.dp = self.dp
+        return rng, best_model, best_state, torch.from_numpy(loss_values).to(data.device)
 
     def to_precision(self, precision: str = "float32"):
         """The B200 path computes in float32 only (nf_model/base.py:212-242 is experimental upstream)."""

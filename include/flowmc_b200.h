@@ -192,10 +192,11 @@ FLOWMC_API int flowmc_flow_loss_grad(const FlowmcFlowDesc* desc, const float* pa
                                      void* workspace, int64_t workspace_bytes, void* stream);
 /* optax.chain(clip_by_global_norm(max_norm), adamw(lr, b1, b2, eps, weight_decay)) applied in place to the flat
  * vectors (all device, n_params floats): params, Adam moments mu / nu.  count = 1-based step number (optax's
- * count after increment); scratch: device, >= 256 floats; gnorm_out: optional device float (pre-clip norm). */
+ * count after increment); hyperparameters are doubles because optax holds them as Python floats (1 - b1 is
+ * formed in double before rounding to float32); scratch: device, >= 256 floats; gnorm_out: optional device float (pre-clip norm). */
 FLOWMC_API int flowmc_clip_adamw(int64_t n_params, float* params, const float* grads, float* mu, float* nu,
-                                 int64_t count, float lr, float b1, float b2, float eps, float weight_decay,
-                                 float max_norm, float* scratch, float* gnorm_out, void* stream);
+                                 int64_t count, double lr, double b1, double b2, double eps, double weight_decay,
+                                 double max_norm, float* scratch, float* gnorm_out, void* stream);
 
 /* ---- training-set plumbing (strategy/train_model.py:66-81, nf_model/base.py:141-144,187-188) --------------- */
 /* jax.random.permutation(key, n) -> out device int32[n] */

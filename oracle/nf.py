@@ -198,7 +198,7 @@ def loss_and_grads(p, x, dtype=torch.float64):
     nW = len(tp["W"])
     g = dict(W=[t.numpy().astype(F32) for t in gs[:nW]], b=[t.numpy().astype(F32) for t in gs[nW:2 * nW]],
              scale=gs[2 * nW].numpy().astype(F32), shift=gs[2 * nW + 1].numpy().astype(F32))
-    return float(loss), g
+    return float(loss.detach()), g
 
 
 # ------------------------------------------------------------------------------ flat layout + optimizer
@@ -276,7 +276,9 @@ def clip_adamw(params, grads, st: AdamWState, lr, b1=0.9, b2=0.999, eps=1e-8, wd
 
 
 def train(p, rng_key, data, st: AdamWState, lr, num_epochs, batch_size, momentum=0.9, grad_dtype=torch.float64):
-    """NFModel.train (base.py:153-210) with the Optimizer's chain.  Returns (best params, best state, losses)."""
+    """NFModel.train (base.py:153-210) with the Optimizer's chain.  Returns (rng, best params, best state,
+    losses); ``st`` is left untouched (the reference's optimiser state is functional)."""
+    st = st.copy()
     data = np.asarray(data, F32)
     N = data.shape[0]
     q = p.copy()
@@ -302,7 +304,7 @@ def train(p, rng_key, data, st: AdamWState, lr, num_epochs, batch_size, momentum
         losses[e] = value
         if losses[e] < best_loss:
             best, best_st, best_loss = q.copy(), st.copy(), losses[e]
-    return best, best_st, losses
+    return key, best, best_st, losses
 
 
 def select_training_data(rng_key, buffer, n_max_examples, history_window):

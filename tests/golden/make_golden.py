@@ -1,0 +1,92 @@
+"""Regenerates tests/golden/*.npz from the oracle (run from the repo root: python tests/golden/make_golden.py).
+
+The reference itself (flowMC on jax) cannot be imported in this container or on the GPU box (jax,
+equinox and optax are absent and there is no network), so these vectors are outputs of the CPU
+restatement under oracle/, NOT of flowMC: "parity unpinned" in the task's vocabulary.  What pins the
+oracle to the reference is listed in DESIGN.md (Random123 threefry KATs, documented
+split(PRNGKey(42)) values, the dual-moon KAT from docs/tutorials/dualmoon.ipynb:65, scipy erfinv,
+float64 autograd of the restated log_prob, and the reference's invariant tests).  The fixtures
+serve two purposes: they freeze the oracle (tests/test_oracle_golden.py fails if a later edit
+changes its results) and give the GPU tests fixed known-answer inputs/outputs that do not
+depend on the oracle code being importable.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import flow as oflow, local as olocal, nf, rng, targets as otargets  # noqa: E402
+from flowutil import random_params  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def flow_case():
+    d, L, hidden, K, n = 5, 3, [16, 16], 8, 24
+    p = random_params(11, d, L, hidden, K)
+    x = (3.0 * np.random.default_rng(3).standard_normal((n, d))).astype(np.float32)
+    x[0, 0], x[1, 2] = 17.0, -23.0
+    y, ld = oflow.forward(p, x)
+    xi, ldi = oflow.inverse(p, x)
+    key = rng.PRNGKey(123)
+    blob = dict(x=x, fwd_y=y, fwd_logdet=ld, inv_x=xi, inv_logdet=ldi, log_prob=oflow.log_prob(p, x),
+                sample_key=key, sample=oflow.sample(p, key, 16), params_flat=nf.flatten(p),
+                shape=np.array([d, L, K] + hidden, np.int32))
+    loss, g = nf.loss_and_grads(p, x)
+    blob.update(loss=np.float32(loss), grad_flat=nf.flatten(g, p))
+    np.savez_compressed(os.path.join(OUT, "flow_d5.npz"), **blob)
+
+
+def init_case():
+    key = rng.PRNGKey(42)
+    p = oflow.init_params(key, 5, 4, [32, 32], 8)
+    np.savez_compressed(os.path.join(OUT, "flow_init_key42.npz"), params_flat=nf.flatten(p),
+                        log_prob_zero=oflow.log_prob(p, np.zeros((1, 5), np.float32)))
+
+
+def local_case():
+    d, n, steps = 5, 8, 12
+    key = rng.PRNGKey(42)
+    ks = rng.split(key, 2)
+    x0 = rng.normal(ks[1], (n, d))
+    packed = otargets.DualMoon.pack(d, None)
+    out = {}
+    for kind, kw in (("MALA", dict(step_size=0.1)), ("GRW", dict(step_size=0.3)),
+                     ("HMC", dict(step_size=0.05, n_leapfrog=4, condition_matrix=np.eye(d, dtype=np.float32)))):
+        k = olocal.make_kernel(kind, **kw)
+        nk, pos, lp, acc, last = olocal.take_serial_steps(ks[0], x0, "dual_moon", packed, k, steps)
+        out.update({f"{kind}_key": nk, f"{kind}_pos": pos, f"{kind}_lp": lp, f"{kind}_acc": acc})
+    np.savez_compressed(os.path.join(OUT, "local_dualmoon_d5.npz"), key=ks[0], x0=x0, **out)
+
+
+def nf_case():
+    d, n, n_steps = 5, 6, 7
+    p = random_params(21, d, 2, [16, 16], 8, gain=1.0, affine=0.0, whiten=False)
+    key = rng.PRNGKey(7)
+    ks = rng.split(key, 2)
+    x0 = rng.normal(ks[1], (n, d))
+    packed = otargets.IsoGaussian.pack(d, 0.5)
+    out = {}
+    for tag, bs in (("simple", 100), ("batched", 3)):
+        nk, pos, lp, acc, last, dbg = nf.take_group_steps(ks[0], x0, p, "iso_gaussian", packed, n_steps, bs)
+        out.update({f"{tag}_key": nk, f"{tag}_pos": pos, f"{tag}_lp": lp, f"{tag}_acc": acc,
+                    f"{tag}_proposals": dbg["proposals"], f"{tag}_lp_nf": dbg["lp_nf_prop"]})
+    np.savez_compressed(os.path.join(OUT, "nf_global_iso_d5.npz"), key=ks[0], x0=x0, params_flat=nf.flatten(p), **out)
+
+
+def rng_case():
+    key = rng.PRNGKey(42)
+    np.savez_compressed(os.path.join(OUT, "rng_key42.npz"), split=rng.split(key, 4), bits=rng.random_bits(key, (16,)),
+                        uniform=rng.uniform(key, (16,)), normal=rng.normal(key, (16,)),
+                        permutation=rng.permutation(key, 2000), choice=rng.choice_with_replacement(key, 1000, 64))
+
+
+if __name__ == "__main__":
+    flow_case(); init_case(); local_case(); nf_case(); rng_case()
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(OUT, f)))
