@@ -219,6 +219,13 @@ FLOWMC_API int flowmc_gather_training_rows(const float* buf, const int32_t* rowm
 FLOWMC_API int flowmc_data_mean_cov(const float* x, int64_t n, int d, float* mean, float* cov, float* scratch,
                                     void* stream);
 
+/* ---- diagnostics ---------------------------------------------------------------------------------------- */
+/* out[128, N] = A[128, K] W[N, K]^T through the tcgen05 path (A in TMEM, W as packed swizzled stages, kind::tf32,
+ * terms = 1: plain TF32, 3: 3xTF32).  Unit-test hook for the operand conventions of the tensor-core flow kernels.
+ * N % 16 == 0 (16..256), K % 32 == 0 (32..128); scratch: device, >= (K/32) * 2 * N * 128 bytes. */
+FLOWMC_API int flowmc_debug_tc_gemm(const float* A, const float* W, int N, int K, int terms, float* out,
+                                    float* scratch, void* stream);
+
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 FLOWMC_API int64_t flowmc_launch_count(void);
 
