@@ -40,6 +40,8 @@ class FlowDesc(C.Structure):
         ("off_data_mean", C.c_int64), ("off_data_cov", C.c_int64), ("off_base_mean", C.c_int64),
         ("off_base_cov", C.c_int64),
         ("n_params", C.c_int64),
+        ("tc_image", C.c_void_p),
+        ("tc_terms", C.c_int),
     ]
 
 
@@ -78,6 +80,8 @@ def _load() -> C.CDLL:
         "flowmc_launch_count": (i64, []),
         "flowmc_local_steps_workspace_bytes": (i64, [i64, i32, i32]),
         "flowmc_flow_desc_init": (i32, [C.POINTER(FlowDesc), i32, i32, i32, C.POINTER(C.c_int), i32, f32, f32]),
+        "flowmc_flow_tc_image_bytes": (i64, [C.POINTER(FlowDesc)]),
+        "flowmc_flow_tc_pack": (i32, [C.POINTER(FlowDesc), vp, vp, vp]),
         "flowmc_flow_forward": (i32, [C.POINTER(FlowDesc), vp, vp, i64, vp, vp, vp]),
         "flowmc_flow_inverse": (i32, [C.POINTER(FlowDesc), vp, vp, i64, vp, vp, vp]),
         "flowmc_flow_log_prob": (i32, [C.POINTER(FlowDesc), vp, vp, i64, vp, vp, vp]),

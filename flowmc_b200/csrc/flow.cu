@@ -111,6 +111,8 @@ int flow_transform(const FlowmcFlowDesc& D, bool inverse, const float* P, const 
                    float* ld, float* layer_inputs, int pre, int post, const uint32_t* keys, Key hk, int64_t rpk,
                    cudaStream_t stream, const int32_t* idx) {
   if (n <= 0) return FLOWMC_OK;
+  if (layer_inputs == nullptr && flow_tc_enabled(D))
+    return flow_transform_tc(D, inverse, P, x, n, y, ld, pre, post, keys, hk, rpk, stream, idx);
 #define FLOWMC_DISPATCH_K(KK)                                                                                      \
   case KK:                                                                                                         \
     return inverse                                                                                                 \

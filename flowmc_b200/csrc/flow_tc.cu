@@ -1,0 +1,551 @@
+// MaskedCouplingRQSpline forward / inverse / log_prob / sample / NF proposals on the sm_100a tensor cores.
+//
+// Reference: src/flowMC/resource/model/nf_model/rqSpline.py:392-504, resource/model/common.py:68-168, and for the
+// proposal mode resource/kernel/NF_proposal.py:130-172.
+//
+// One CTA owns 128 samples (= the 128 TMEM lanes) and walks ALL coupling layers with the tile on chip:
+//   * the conditioner's three Linear layers are tcgen05.mma kind::tf32 GEMMs with M = 128:
+//       A (activations)  lives in TENSOR MEMORY (written by the epilogue warps with tcgen05.st), so shared-memory
+//                        bandwidth only carries B;
+//       B (weights)      is streamed from a pre-packed, pre-swizzled global image (tc_pack_flow_kernel) with
+//                        cp.async.bulk (TMA engine) through a ring of 32 KB shared-memory stages;
+//       D (accumulators) two 128-column TMEM slots, so the MMAs of spline chunk c+1 overlap the epilogue of chunk c.
+//     3xTF32: every fp32 operand is split hi + lo and a_hi b_hi + a_lo b_hi + a_hi b_lo is accumulated in fp32, which
+//     reproduces the fp32 product to ~2^-21 -- the results stay inside the 1e-5 parity tolerance (tc_terms = 1 runs
+//     plain TF32 at 3x the tensor rate with ~1e-3 relative error in the spline parameters).
+//   * the rational-quadratic spline is the last GEMM's EPILOGUE: the output columns are ordered feature-major, a
+//     chunk of 4 features (100 of 112 columns) is read back with tcgen05.ld (TMEM lane = sample) and softmax /
+//     cumsum / softplus / bin search / transform / log-det run in registers (flow_common.cuh), exactly the code the
+//     CUDA-core path uses.  Only the transformed half of W3 is ever loaded.
+//   * warp roles: warps 0-7 epilogue (two threads per sample row, splitting columns / features), warp 8 weight
+//     producer (one elected lane issues the bulk copies), warp 9 MMA issuer (one elected lane).
+//   TMEM map (512 columns): [0,128) A hi | [128,256) A lo | [256,384) acc slot 0 | [384,512) acc slot 1.
+#include <cstring>
+#include <string>
+
+#include "flow_tile.cuh"
+#include "registry.h"
+#include "tc_common.cuh"
+
+namespace flowmc {
+
+constexpr int TC_M = 128;          // samples per CTA
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI = TC_EPI_WARPS * 32;
+constexpr int TC_THREADS = TC_EPI + 64;
+constexpr int TC_STAGES = 4;
+constexpr int TC_STAGE_BYTES = 2 * 128 * 128;  // hi + lo images of up to 128 rows x 128 B
+constexpr int TC_MAX_ITEMS = 40;
+
+enum : int { TC_FWD = 0, TC_INV = 1, TC_NF = 2 };
+
+struct TcItem {
+  int kind;      // 0: hidden Linear (+tanh), 1: chunk of spline features
+  int K;         // reduction length
+  int n_kc;      // ceil(K / 32) stages
+  int npad;      // MMA N (multiple of 16, <= 128) = rows per stage image
+  int lin;       // hidden: index of the Linear; chunk: first transformed-feature ordinal
+  int n_feat;    // chunk: features in it
+  uint32_t off;  // byte offset of the item's first stage from the layer's image base
+  int pad_;
+};
+struct TcProgram {
+  int n_items[2];  // by layer parity (which features are transformed alternates, rqSpline.py:434)
+  uint32_t layer_bytes[2];
+  TcItem items[2][TC_MAX_ITEMS];
+};
+
+static bool tc_supported(const FlowmcFlowDesc& D) {
+  if (D.n_features < 2 || D.n_features > 128) return false;
+  if (D.num_bins != 4 && D.num_bins != 8 && D.num_bins != 16) return false;
+  for (int i = 1; i < D.n_linear; ++i)
+    if (D.dims[i] > 128 || (D.dims[i] % 16) != 0) return false;
+  return true;
+}
+
+static int tc_build_program(const FlowmcFlowDesc& D, TcProgram* P) {
+  const int d = D.n_features, NP = 3 * D.num_bins + 1, nh = D.n_linear - 1;
+  int fc = 128 / NP;
+  fc &= ~1;  // even, so that the two epilogue threads of a row split a chunk evenly
+  for (int p = 0; p < 2; ++p) {
+    int n = 0;
+    uint32_t off = 0;
+    for (int i = 0; i < nh; ++i) {
+      TcItem& it = P->items[p][n++];
+      it.kind = 0; it.K = D.dims[i]; it.n_kc = (it.K + 31) / 32; it.npad = D.dims[i + 1]; it.lin = i; it.n_feat = 0;
+      it.off = off; it.pad_ = 0;
+      off += (uint32_t)it.n_kc * 2u * it.npad * 128u;
+    }
+    const int ntf = (d - p + 1) / 2;
+    for (int c0 = 0; c0 < ntf; c0 += fc) {
+      if (n >= TC_MAX_ITEMS) return FLOWMC_ERR_UNSUPPORTED;
+      TcItem& it = P->items[p][n++];
+      it.kind = 1; it.K = D.dims[nh]; it.n_kc = (it.K + 31) / 32; it.lin = c0;
+      it.n_feat = (ntf - c0 < fc) ? ntf - c0 : fc;
+      it.npad = (it.n_feat * NP + 15) & ~15;
+      it.off = off; it.pad_ = 0;
+      off += (uint32_t)it.n_kc * 2u * it.npad * 128u;
+    }
+    P->n_items[p] = n;
+    P->layer_bytes[p] = off;
+  }
+  return FLOWMC_OK;
+}
+
+static int64_t tc_image_bytes(const FlowmcFlowDesc& D, const TcProgram& P) {
+  int64_t b = 0;
+  for (int l = 0; l < D.n_layers; ++l) b += P.layer_bytes[l & 1];
+  return b;
+}
+
+__device__ __forceinline__ int64_t tc_layer_base(const FlowmcFlowDesc& D, const TcProgram& P, int l) {
+  // layers alternate parity 0,1,0,1,...
+  return (int64_t)((l + 1) / 2) * P.layer_bytes[0] + (int64_t)(l / 2) * P.layer_bytes[1];
+}
+
+// blob -> packed image.  grid = (items, layers)
+__global__ void tc_pack_flow_kernel(const FlowmcFlowDesc D, const TcProgram P, const float* __restrict__ params,
+                                    uint8_t* __restrict__ image) {
+  const int l = blockIdx.y, p = l & 1;
+  if ((int)blockIdx.x >= P.n_items[p]) return;
+  const TcItem it = P.items[p][blockIdx.x];
+  const int NP = 3 * D.num_bins + 1, nh = D.n_linear - 1;
+  const float* PL = params + (int64_t)l * D.layer_stride;
+  float* dst = reinterpret_cast<float*>(image + tc_layer_base(D, P, l) + it.off);
+  const int per_stage = it.npad * 32;
+  const int total = it.n_kc * per_stage;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int kc = i / per_stage, rem = i - kc * per_stage;
+    const int n = rem >> 5, kk = rem & 31;
+    const int k = kc * 32 + kk;
+    float w = 0.0f;
+    if (k < it.K) {
+      if (it.kind == 0) {
+        if (n < D.dims[it.lin + 1]) w = PL[D.off_W[it.lin] + (int64_t)n * it.K + k];
+      } else if (n < it.n_feat * NP) {
+        const int fi = n / NP, r = n - fi * NP;
+        const int f = p + 2 * (it.lin + fi);
+        w = PL[D.off_W[nh] + ((int64_t)f * NP + r) * it.K + k];
+      }
+    }
+    uint32_t hi, lo;
+    tc::split_tf32(w, hi, lo);
+    float* stage = dst + (int64_t)kc * 2 * per_stage;
+    const int o = tc::packed_b_offset(n, kk) >> 2;
+    stage[o] = __uint_as_float(hi);
+    stage[per_stage + o] = __uint_as_float(lo);
+  }
+}
+
+struct TcArgs {
+  const float* params;
+  const uint8_t* image;
+  const float* xin;       // [n, d] (FWD / INV with PRE_NONE / PRE_WHITEN)
+  const int32_t* idx;     // optional row gather for xin
+  float* yout;            // [n, d] transformed rows (POST_NONE / POST_UNWHITEN; NF: the proposals)
+  float* ldout;           // [n] log-det, or log_prob with POST_BASE_LOGP (NF: flow log-prob of the proposals)
+  int64_t n;
+  int pre, post, terms;
+  const uint32_t* keys;   // PRE_NORMAL: device keys [ceil(n / rows_per_key), 2] or NULL -> host_key
+  Key host_key;
+  int64_t rows_per_key;
+  // NF mode: per-row key schedule of NFProposal.sample_flow
+  Key subkey;
+  const uint32_t* chain_keys;
+  int64_t chain_offset;
+  int n_steps, n_batch, n_sample;
+};
+
+struct TcSmem {
+  uint64_t stage_full[TC_STAGES], stage_empty[TC_STAGES], acc_full[2], acc_empty[2], a_ready;
+  uint32_t tmem_base;
+  float ldpart[2][TC_M];
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI) : "memory"); }
+
+template <int KB, int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlowDesc D, const TcProgram PR,
+                                                                const TcArgs a) {
+  constexpr int NP = 3 * KB + 1;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* stages = smem;                                             // TC_STAGES x TC_STAGE_BYTES, 1024-aligned
+  TcSmem* S = reinterpret_cast<TcSmem*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  const int d = D.n_features;
+  const int xs_stride = d + 1;
+  float* xs = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES + ((sizeof(TcSmem) + 15) & ~15));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* P = a.params;
+  const int L = D.n_layers, nh = D.n_linear - 1;
+  const int n_pass = (MODE == TC_NF) ? 2 : 1;
+  const int64_t row0 = (int64_t)blockIdx.x * TC_M;
+
+  if (warp == 9 && lane == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) {
+      tc::mbar_init(&S->stage_full[i], 1);
+      tc::mbar_init(&S->stage_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&S->acc_full[i], 1);
+      tc::mbar_init(&S->acc_empty[i], TC_EPI);
+    }
+    tc::mbar_init(&S->a_ready, TC_EPI);
+    tc::fence_mbar_init();
+  }
+  if (warp == 8) tc::tmem_alloc<512>(&S->tmem_base);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tbase = S->tmem_base;
+  const uint32_t t_ahi = tbase, t_alo = tbase + 128;
+
+  if (warp == 8) {
+    // ===== weight producer =====================================================================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const bool inv = (MODE == TC_INV) || (MODE == TC_NF && pass == 0);
+        for (int li = 0; li < L; ++li) {
+          const int l = inv ? L - 1 - li : li, p = l & 1;
+          const uint8_t* lbase = a.image + tc_layer_base(D, PR, l);
+          for (int ii = 0; ii < PR.n_items[p]; ++ii) {
+            const TcItem& it = PR.items[p][ii];
+            const uint32_t bytes = 2u * it.npad * 128u;
+            for (int kc = 0; kc < it.n_kc; ++kc) {
+              tc::mbar_wait(&S->stage_empty[s], ph ^ 1);
+              tc::mbar_arrive_expect_tx(&S->stage_full[s], bytes);
+              tc::bulk_g2s(stages + (size_t)s * TC_STAGE_BYTES, lbase + it.off + (size_t)kc * bytes, bytes,
+                           &S->stage_full[s]);
+              if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===== MMA issuer ==========================================================================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0, seq = 0, a_ph = 0;
+      for (int pass = 0; pass < n_pass; ++pass) {
+        const bool inv = (MODE == TC_INV) || (MODE == TC_NF && pass == 0);
+        for (int li = 0; li < L; ++li) {
+          const int l = inv ? L - 1 - li : li, p = l & 1;
+          for (int ii = 0; ii < PR.n_items[p]; ++ii) {
+            const TcItem& it = PR.items[p][ii];
+            if (it.kind == 0 || it.lin == 0) {  // a new A operand: masked x, h1, ..., h_last
+              tc::mbar_wait(&S->a_ready, a_ph);
+              a_ph ^= 1;
+            }
+            const uint32_t slot = seq & 1;
+            tc::mbar_wait(&S->acc_empty[slot], ((seq >> 1) & 1) ^ 1);
+            tc::tc_fence_after();
+            const uint32_t t_acc = tbase + 256 + slot * 128;
+            const uint32_t idesc = tc::make_idesc_tf32(TC_M, it.npad);
+            uint32_t accum = 0;
+            for (int kc = 0; kc < it.n_kc; ++kc) {
+              tc::mbar_wait(&S->stage_full[s], ph);
+              tc::tc_fence_after();
+              const uint32_t b_hi = tc::smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
+              const uint32_t b_lo = b_hi + it.npad * 128;
+              const int ksteps = min(4, (it.K - kc * 32 + 7) >> 3);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t acol = kc * 32 + ks * 8;
+                const uint64_t dhi = tc::make_b_desc(b_hi + ks * 32);
+                tc::mma_tf32_ts(t_acc, t_ahi + acol, dhi, idesc, accum);
+                accum = 1;
+                if (a.terms == 3) {
+                  tc::mma_tf32_ts(t_acc, t_alo + acol, dhi, idesc, 1);
+                  tc::mma_tf32_ts(t_acc, t_ahi + acol, tc::make_b_desc(b_lo + ks * 32), idesc, 1);
+                }
+              }
+              tc::mma_commit(&S->stage_empty[s]);
+              if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+            }
+            tc::mma_commit(&S->acc_full[slot]);
+            ++seq;
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue warps: two threads per sample row ==========================================
+    const int q = warp & 3, hf = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int64_t grow = row0 + row;
+    const int64_t r = min(grow, a.n - 1);
+    float* xr = xs + row * xs_stride;
+    // this thread's share of the d features (affine / operand writes / pre / post): 8-column groups
+    const int g_all = (d + 7) >> 3;
+    const int g_lo = hf ? (g_all + 1) / 2 : 0, g_hi = hf ? g_all : (g_all + 1) / 2;
+    const int j_lo = g_lo * 8, j_hi = min(d, g_hi * 8);
+
+    // ---- load / generate the tile ------------------------------------------------------------
+    if (MODE == TC_NF) {
+      const int64_t c = r / a.n_steps;
+      const int t = (int)(r - c * a.n_steps);
+      Key ck = a.chain_keys ? Key{a.chain_keys[2 * c], a.chain_keys[2 * c + 1]}
+                            : split_at(a.subkey, (uint64_t)(a.chain_offset + c));
+      Key key = split_at(ck, 1);
+      int idx = t;
+      if (a.n_batch > 0) {
+        const int b = t / a.n_sample;
+        for (int i = 0; i < b; ++i) key = split_at(key, 0);
+        key = split_at(key, 1);
+        idx = t - b * a.n_sample;
+      }
+      for (int j = j_lo; j < j_hi; ++j) {
+        const float z = bits_to_normal(bits_at(key, (uint64_t)((uint32_t)idx * (uint32_t)d + (uint32_t)j)));
+        xr[j] = P[D.off_base_mean + j] + z * sqrtf(P[D.off_base_cov + (int64_t)j * d + j]);
+      }
+    } else if (a.pre == PRE_NORMAL) {
+      const int64_t kidx = r / a.rows_per_key;
+      const Key key = a.keys ? Key{a.keys[2 * kidx], a.keys[2 * kidx + 1]} : a.host_key;
+      for (int j = j_lo; j < j_hi; ++j) {
+        const float z = bits_to_normal(bits_at(key, (uint64_t)((r - kidx * a.rows_per_key) * d + j)));
+        xr[j] = P[D.off_base_mean + j] + z * sqrtf(P[D.off_base_cov + (int64_t)j * d + j]);
+      }
+    } else {
+      const float* src = a.xin + (a.idx ? (int64_t)a.idx[r] : r) * d;
+      for (int j = j_lo; j < j_hi; ++j) {
+        float v = src[j];
+        if (a.pre == PRE_WHITEN) v = (v - P[D.off_data_mean + j]) / sqrtf(P[D.off_data_cov + (int64_t)j * d + j]);
+        xr[j] = v;
+      }
+    }
+    float ldacc = 0.0f;
+    uint32_t seq = 0;
+
+    for (int pass = 0; pass < n_pass; ++pass) {
+      const bool inv = (MODE == TC_INV) || (MODE == TC_NF && pass == 0);
+      for (int li = 0; li < L; ++li) {
+        const int l = inv ? L - 1 - li : li, p = l & 1;
+        const float* PL = P + (int64_t)l * D.layer_stride;
+        const float scale = PL[D.off_scale], shift = PL[D.off_shift];
+        // ---- ScalarAffine (rqSpline.py:435-436) + A operand = x * mask, hi / lo ------------------
+        {
+          const float e = inv ? expf(-scale) : expf(scale);
+          for (int g = g_lo; g < g_hi; ++g) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int j = g * 8 + u;
+              float v = 0.0f;
+              if (j < d) {
+                v = xr[j];
+                v = inv ? v * e - shift : (v + shift) * e;
+                xr[j] = v;
+                if (((j + l) & 1) == 0) v = 0.0f;  // transformed features do not feed the conditioner
+              }
+              tc::split_tf32(v, hi[u], lo[u]);
+            }
+            tc::tmem_st8(t_ahi + lane_base + g * 8, hi);
+            tc::tmem_st8(t_alo + lane_base + g * 8, lo);
+          }
+          if (hf == 0) ldacc += inv ? -(float)d * scale : (float)d * scale;
+          tc::tmem_wait_st();
+          tc::tc_fence_before();
+          tc::mbar_arrive(&S->a_ready);
+          epi_bar();  // the row's other thread reads these x values in the spline stage
+        }
+        for (int ii = 0; ii < PR.n_items[p]; ++ii) {
+          const TcItem& it = PR.items[p][ii];
+          const uint32_t slot = seq & 1;
+          const uint32_t t_acc = tbase + 256 + slot * 128 + lane_base;
+          tc::mbar_wait(&S->acc_full[slot], (seq >> 1) & 1);
+          tc::tc_fence_after();
+          if (it.kind == 0) {
+            // ---- tanh(acc + b) -> next A operand (this thread: half of the columns) ----------------
+            const int N = it.npad;               // hidden width, multiple of 16
+            const int c_lo = hf ? (N / 16 + 1) / 2 * 16 : 0, c_hi = hf ? N : (N / 16 + 1) / 2 * 16;
+            const float* bias = PL + D.off_b[it.lin];
+            for (int c = c_lo; c < c_hi; c += 16) {
+              float v[16];
+              tc::tmem_ld16(t_acc + c, v);
+              tc::tmem_wait_ld();
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int u = 0; u < 16; ++u) tc::split_tf32(tanhf(v[u] + __ldg(bias + c + u)), hi[u], lo[u]);
+              tc::tmem_st8(t_ahi + lane_base + c, hi);
+              tc::tmem_st8(t_ahi + lane_base + c + 8, hi + 8);
+              tc::tmem_st8(t_alo + lane_base + c, lo);
+              tc::tmem_st8(t_alo + lane_base + c + 8, lo + 8);
+            }
+            tc::tmem_wait_st();
+            tc::tc_fence_before();
+            tc::mbar_arrive(&S->acc_empty[slot]);
+            tc::mbar_arrive(&S->a_ready);
+          } else {
+            // ---- spline epilogue: this thread's half of the chunk's features ------------------------
+            const int nf = it.n_feat;
+            const int i_lo = hf ? (nf + 1) / 2 : 0, i_hi = hf ? nf : (nf + 1) / 2;
+            const float* bl = PL + D.off_b[nh];
+            for (int i = i_lo; i < i_hi; ++i) {
+              const int f = p + 2 * (it.lin + i);
+              float v[32];
+              tc::tmem_ld32(t_acc + i * NP, v);
+              tc::tmem_wait_ld();
+              float raw[NP];
+#pragma unroll
+              for (int u = 0; u < NP && u < 32; ++u) raw[u] = v[u] + __ldg(bl + f * NP + u);
+              if (NP > 32) {
+                float v2[32];
+                tc::tmem_ld32(t_acc + i * NP + 32, v2);
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int u = 32; u < NP; ++u) raw[u] = v2[u - 32] + __ldg(bl + f * NP + u);
+              }
+              RQ qp;
+              float t;
+              rq_params<KB>(raw, D.range_min, D.range_max, qp);
+              xr[f] = inv ? rq_inverse<KB>(qp, xr[f], t) : rq_forward<KB>(qp, xr[f], t);
+              ldacc += t;
+            }
+            tc::tc_fence_before();
+            tc::mbar_arrive(&S->acc_empty[slot]);
+          }
+          ++seq;
+        }
+        epi_bar();  // both threads of a row see each other's feature updates
+      }
+      if (MODE == TC_NF && pass == 0) {
+        // proposal = inverse * sqrt(diag data_cov) + data_mean (rqSpline.py:495); keep it; re-whiten (rqSpline.py:501)
+        for (int j = j_lo; j < j_hi; ++j) {
+          const float sd = sqrtf(P[D.off_data_cov + (int64_t)j * d + j]);
+          const float mu = P[D.off_data_mean + j];
+          const float x = xr[j] * sd + mu;
+          if (grow < a.n) __stcs(a.yout + grow * d + j, x);
+          xr[j] = (x - mu) / sd;
+        }
+        ldacc = 0.0f;
+        epi_bar();
+      }
+    }
+
+    // ---- epilogue of the tile ------------------------------------------------------------------
+    S->ldpart[hf][row] = ldacc;
+    epi_bar();
+    const int post = (MODE == TC_NF) ? POST_BASE_LOGP : a.post;
+    if (post == POST_BASE_LOGP) {
+      if (hf == 0 && grow < a.n)
+        a.ldout[grow] = (S->ldpart[0][row] + S->ldpart[1][row]) + base_log_prob(D, P, xr);
+    } else {
+      if (grow < a.n) {
+        for (int j = j_lo; j < j_hi; ++j) {
+          float v = xr[j];
+          if (post == POST_UNWHITEN) v = v * sqrtf(P[D.off_data_cov + (int64_t)j * d + j]) + P[D.off_data_mean + j];
+          a.yout[grow * d + j] = v;
+        }
+        if (hf == 0 && a.ldout != nullptr) a.ldout[grow] = S->ldpart[0][row] + S->ldpart[1][row];
+      }
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  tc::tc_fence_after();
+  if (warp == 8) tc::tmem_dealloc<512>(tbase);
+}
+
+template <int KB, int MODE>
+static int launch_tc(const FlowmcFlowDesc& D, const TcProgram& PR, const TcArgs& a, cudaStream_t stream) {
+  auto kern = flow_tc_kernel<KB, MODE>;
+  const size_t bytes = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + ((sizeof(TcSmem) + 15) & ~15) +
+                       (size_t)TC_M * (D.n_features + 1) * sizeof(float);
+  static size_t configured = 0;
+  if (bytes > configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+      flowmc_set_error("flow (tensor-core path): cannot configure shared memory");
+      return FLOWMC_ERR_CUDA;
+    }
+    configured = bytes;
+  }
+  kern<<<(unsigned)((a.n + TC_M - 1) / TC_M), TC_THREADS, bytes, stream>>>(D, PR, a);
+  flowmc_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    flowmc_set_error(cudaGetErrorString(e));
+    return FLOWMC_ERR_CUDA;
+  }
+  return FLOWMC_OK;
+}
+
+template <int MODE>
+static int dispatch_tc(const FlowmcFlowDesc& D, const TcProgram& PR, const TcArgs& a, cudaStream_t stream) {
+  switch (D.num_bins) {
+    case 4: return launch_tc<4, MODE>(D, PR, a, stream);
+    case 8: return launch_tc<8, MODE>(D, PR, a, stream);
+    case 16: return launch_tc<16, MODE>(D, PR, a, stream);
+  }
+  return FLOWMC_ERR_UNSUPPORTED;
+}
+
+// true if the descriptor asks for (and the model shape allows) the tensor-core path
+bool flow_tc_enabled(const FlowmcFlowDesc& D) { return D.tc_image != nullptr && D.tc_terms != 0 && tc_supported(D); }
+
+int flow_transform_tc(const FlowmcFlowDesc& D, bool inverse, const float* P, const float* x, int64_t n, float* y,
+                      float* ld, int pre, int post, const uint32_t* keys, Key hk, int64_t rpk, cudaStream_t stream,
+                      const int32_t* idx) {
+  if (n <= 0) return FLOWMC_OK;
+  TcProgram PR;
+  if (int rc = tc_build_program(D, &PR)) return rc;
+  TcArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.params = P; a.image = static_cast<const uint8_t*>(D.tc_image); a.xin = x; a.idx = idx; a.yout = y; a.ldout = ld;
+  a.n = n; a.pre = pre; a.post = post; a.terms = D.tc_terms == 1 ? 1 : 3; a.keys = keys; a.host_key = hk;
+  a.rows_per_key = rpk;
+  return inverse ? dispatch_tc<TC_INV>(D, PR, a, stream) : dispatch_tc<TC_FWD>(D, PR, a, stream);
+}
+
+int flow_nf_propose_tc(const FlowmcFlowDesc& D, const float* P, Key subkey, const uint32_t* chain_keys,
+                       int64_t chain_offset, int64_t n_chains, int n_steps, int n_batch, int n_sample, float* props,
+                       float* lp_nf, cudaStream_t stream) {
+  TcProgram PR;
+  if (int rc = tc_build_program(D, &PR)) return rc;
+  TcArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.params = P; a.image = static_cast<const uint8_t*>(D.tc_image); a.yout = props; a.ldout = lp_nf;
+  a.n = n_chains * n_steps; a.terms = D.tc_terms == 1 ? 1 : 3;
+  a.subkey = subkey; a.chain_keys = chain_keys; a.chain_offset = chain_offset;
+  a.n_steps = n_steps; a.n_batch = n_batch; a.n_sample = n_sample;
+  return dispatch_tc<TC_NF>(D, PR, a, stream);
+}
+
+}  // namespace flowmc
+
+extern "C" {
+
+int64_t flowmc_flow_tc_image_bytes(const FlowmcFlowDesc* D) {
+  using namespace flowmc;
+  if (!D || !tc_supported(*D)) return 0;
+  TcProgram PR;
+  if (tc_build_program(*D, &PR)) return 0;
+  return tc_image_bytes(*D, PR);
+}
+
+int flowmc_flow_tc_pack(const FlowmcFlowDesc* D, const float* params, void* image, void* stream) {
+  using namespace flowmc;
+  if (!D || !params || !image) {
+    flowmc_set_error("flow_tc_pack: null argument");
+    return FLOWMC_ERR_INVALID;
+  }
+  if (!tc_supported(*D)) {
+    flowmc_set_error("flow_tc_pack: model shape not supported by the tensor-core path (need n_features <= 128, hidden "
+                     "widths multiples of 16 and <= 128)");
+    return FLOWMC_ERR_UNSUPPORTED;
+  }
+  TcProgram PR;
+  if (int rc = tc_build_program(*D, &PR)) return rc;
+  const int items = PR.n_items[0] > PR.n_items[1] ? PR.n_items[0] : PR.n_items[1];
+  tc_pack_flow_kernel<<<dim3(items, D->n_layers), 256, 0, (cudaStream_t)stream>>>(*D, PR, params,
+                                                                                  static_cast<uint8_t*>(image));
+  flowmc_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    flowmc_set_error(cudaGetErrorString(e));
+    return FLOWMC_ERR_CUDA;
+  }
+  return FLOWMC_OK;
+}
+
+}  // extern "C"

@@ -57,6 +57,15 @@ int flow_transform(const FlowmcFlowDesc& D, bool inverse, const float* P, const 
                    float* ld, float* layer_inputs, int pre, int post, const uint32_t* keys, Key hk, int64_t rpk,
                    cudaStream_t stream, const int32_t* idx = nullptr);
 
+// tensor-core path (flow_tc.cu)
+bool flow_tc_enabled(const FlowmcFlowDesc& D);
+int flow_transform_tc(const FlowmcFlowDesc& D, bool inverse, const float* P, const float* x, int64_t n, float* y,
+                      float* ld, int pre, int post, const uint32_t* keys, Key hk, int64_t rpk, cudaStream_t stream,
+                      const int32_t* idx);
+int flow_nf_propose_tc(const FlowmcFlowDesc& D, const float* P, Key subkey, const uint32_t* chain_keys,
+                       int64_t chain_offset, int64_t n_chains, int n_steps, int n_batch, int n_sample, float* props,
+                       float* lp_nf, cudaStream_t stream);
+
 // out[s][n] = tanh(sum_k in[s][k] W[n][k] + b[n]) for the 64-sample tile; in/out in shared memory
 __device__ __forceinline__ void dense_tanh_stage(const float* __restrict__ in_s, int in_stride, int Kdim,
                                                  const float* __restrict__ W, const float* __restrict__ b, int N,

@@ -250,13 +250,18 @@ int flowmc_nf_global_steps(const FlowmcFlowDesc* D, const float* params, int tar
                               POST_BASE_LOGP, nullptr, Key{0, 0}, 1, stream))
     return rc;
   int rc;
-  switch (D->num_bins) {
-    case 4: rc = launch_propose<4>(*D, params, a, props, lp_nf_prop, stream); break;
-    case 8: rc = launch_propose<8>(*D, params, a, props, lp_nf_prop, stream); break;
-    case 16: rc = launch_propose<16>(*D, params, a, props, lp_nf_prop, stream); break;
-    default:
-      flowmc_set_error("flow: num_bins must be 4, 8 or 16");
-      return FLOWMC_ERR_UNSUPPORTED;
+  if (flow_tc_enabled(*D)) {
+    rc = flow_nf_propose_tc(*D, params, a.subkey, a.chain_keys, a.chain_offset, a.n_chains, a.n_steps, a.n_batch,
+                            a.n_sample, props, lp_nf_prop, stream);
+  } else {
+    switch (D->num_bins) {
+      case 4: rc = launch_propose<4>(*D, params, a, props, lp_nf_prop, stream); break;
+      case 8: rc = launch_propose<8>(*D, params, a, props, lp_nf_prop, stream); break;
+      case 16: rc = launch_propose<16>(*D, params, a, props, lp_nf_prop, stream); break;
+      default:
+        flowmc_set_error("flow: num_bins must be 4, 8 or 16");
+        return FLOWMC_ERR_UNSUPPORTED;
+    }
   }
   if (rc) return rc;
   if (int rc2 = vt.eval(target_data, props, rows, d, lp_prop, nullptr, stream)) return rc2;

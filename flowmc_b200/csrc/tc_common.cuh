@@ -113,12 +113,17 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 }
 
 // ---- operand split -----------------------------------------------------------------------------
-// x = hi + lo with hi = x truncated to tf32 (10 explicit mantissa bits); lo = x - hi exactly (fp32), of which the
-// tensor core again keeps the leading 11 significant bits.  hi*hi + lo*hi + hi*lo reproduces the fp32 product to
-// ~2^-21 relative.
+// x = hi + lo with hi = x rounded to nearest tf32 (10 explicit mantissa bits, cvt.rna) and lo = the exact fp32
+// remainder (|lo| <= 2^-11 |x|) again rounded to nearest tf32, so hi + lo carries x to ~2^-23.
+// a_hi b_hi + a_lo b_hi + a_hi b_lo then reproduces the fp32 product to ~2^-22 relative (the dropped a_lo b_lo).
+__device__ __forceinline__ uint32_t to_tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
+  hi = to_tf32_rn(x);
+  lo = to_tf32_rn(x - __uint_as_float(hi));
 }
 
 // ---- UMMA descriptors --------------------------------------------------------------------------

@@ -43,6 +43,7 @@ class NFProposal(ProposalBase):
         dev = x0.device
         if d != self.model.n_features:
             raise ValueError(f"flow has {self.model.n_features} features, chains have {d}")
+        self.model.prepare()
         ws_bytes = int(lib.flowmc_nf_global_steps_workspace_bytes(n, d, n_steps))
         if self._workspace is None or self._workspace.numel() < ws_bytes or self._workspace.device != dev:
             self._workspace = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)

@@ -16,6 +16,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import math
+import os
 
 import numpy as np
 import torch
@@ -69,6 +70,10 @@ class MaskedCouplingRQSpline(NFModel):
                 torch.atleast_2d(torch.as_tensor(kwargs["data_cov"], dtype=torch.float32)))
         if key is not None:
             self._init_weights(np.asarray(key, dtype=np.uint32))
+        # execution path of the conditioner GEMMs: 3 = tcgen05 3xTF32 (default where the shape allows; fp32-grade),
+        # 1 = tcgen05 plain TF32 (fast, ~1e-3 relative), 0 = fp32 CUDA cores.  FLOWMC_FLOW_TC overrides the default.
+        self.tc_terms = int(os.environ.get("FLOWMC_FLOW_TC", "3"))
+        self._tc_image = None
 
     # ---- parameter blob views ---------------------------------------------------------------
     def _view(self, off: int, shape, layer: int | None = None) -> torch.Tensor:
@@ -128,6 +133,25 @@ class MaskedCouplingRQSpline(NFModel):
             self.weight(l, n_lin - 1).copy_(frandom.uniform(wkey, (dm[-1], dm[-2]), -lim, lim, device=dev))
             self.bias(l, n_lin - 1).copy_(frandom.uniform(bkey, (dm[-1],), -lim, lim, device=dev))
 
+    # ---- tensor-core weight image -------------------------------------------------------------
+    def tc_supported(self) -> bool:
+        return int(lib.flowmc_flow_tc_image_bytes(C.byref(self.desc))) > 0
+
+    def prepare(self):
+        """Refresh the packed tf32 hi/lo weight image the tcgen05 kernels stream (call after params change;
+        every public method does).  Falls back to the fp32 CUDA-core kernels -- same results within the
+        parity tolerance -- when the shape is outside the tensor-core path's limits or tc_terms == 0."""
+        nbytes = int(lib.flowmc_flow_tc_image_bytes(C.byref(self.desc))) if self.tc_terms else 0
+        if nbytes == 0:
+            self.desc.tc_image, self.desc.tc_terms = None, 0
+            return
+        if self._tc_image is None or self._tc_image.numel() != nbytes:
+            self._tc_image = torch.empty(nbytes, dtype=torch.uint8, device=self.params.device)
+        with torch.cuda.device(self.params.device):
+            check(lib.flowmc_flow_tc_pack(C.byref(self.desc), self.params.data_ptr(), self._tc_image.data_ptr(),
+                                          _stream()))
+        self.desc.tc_image, self.desc.tc_terms = self._tc_image.data_ptr(), int(self.tc_terms)
+
     # ---- bijection ---------------------------------------------------------------------------
     def _prep(self, x):
         x = torch.as_tensor(x, dtype=torch.float32)
@@ -141,6 +165,7 @@ class MaskedCouplingRQSpline(NFModel):
 
     def _transform(self, fn, x):
         x2, single, lead = self._prep(x)
+        self.prepare()
         n = x2.shape[0]
         y = torch.empty_like(x2)
         ld = torch.empty(n, dtype=torch.float32, device=x2.device)
@@ -165,6 +190,7 @@ class MaskedCouplingRQSpline(NFModel):
     def log_prob(self, x):
         """rqSpline.py:498-504."""
         x2, single, lead = self._prep(x)
+        self.prepare()
         n = x2.shape[0]
         lp = torch.empty(n, dtype=torch.float32, device=x2.device)
         with torch.cuda.device(x2.device):
@@ -175,6 +201,7 @@ class MaskedCouplingRQSpline(NFModel):
     def sample(self, rng_key, n_samples: int):
         """rqSpline.py:490-496: base.sample(key, n) -> inverse -> un-whiten."""
         key = np.ascontiguousarray(rng_key, dtype=np.uint32)
+        self.prepare()
         out = torch.empty((int(n_samples), self._n_features), dtype=torch.float32, device=self.params.device)
         with torch.cuda.device(out.device):
             check(lib.flowmc_flow_sample(C.byref(self.desc), self.params.data_ptr(), None,
@@ -211,4 +238,5 @@ class MaskedCouplingRQSpline(NFModel):
         m = MaskedCouplingRQSpline(self._n_features, self.n_layers, self.hidden_size, self.num_bins, None,
                                    self.spline_range, device=self.params.device)
         m.params.copy_(self.params)
+        m.tc_terms = self.tc_terms
         return m

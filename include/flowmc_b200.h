@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FLOWMC_ABI_VERSION 1
+#define FLOWMC_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define FLOWMC_API __attribute__((visibility("default")))
@@ -132,11 +132,23 @@ typedef struct FlowmcFlowDesc {
   int64_t layer_stride;
   int64_t off_data_mean, off_data_cov, off_base_mean, off_base_cov;
   int64_t n_params; /* total floats in the blob */
+  /* execution path: tc_image == NULL or tc_terms == 0 -> fp32 CUDA-core kernels; otherwise the tcgen05 kernels
+   * read the conditioner weights from tc_image (device, flowmc_flow_tc_image_bytes() bytes, refreshed with
+   * flowmc_flow_tc_pack() whenever params change).  tc_terms = 3: 3xTF32 (fp32-grade, inside the 1e-5 parity
+   * tolerance), 1: plain TF32 (about 1e-3 relative in the spline parameters). */
+  const void* tc_image;
+  int tc_terms;
 } FlowmcFlowDesc;
 
 /* fills `desc` for (n_features, n_layers, hidden[n_hidden], num_bins, spline range) */
 FLOWMC_API int flowmc_flow_desc_init(FlowmcFlowDesc* desc, int n_features, int n_layers, int n_hidden,
                                      const int* hidden, int num_bins, float range_min, float range_max);
+
+/* tensor-core weight image: size for a model shape (0 if the shape is not supported by the tcgen05 path:
+ * n_features <= 128, hidden widths multiples of 16 and <= 128, num_bins in {4, 8, 16}) and the packing kernel
+ * (splits every weight into tf32 hi + lo and lays the rows out as SWIZZLE_128B K-major UMMA stages) */
+FLOWMC_API int64_t flowmc_flow_tc_image_bytes(const FlowmcFlowDesc* desc);
+FLOWMC_API int flowmc_flow_tc_pack(const FlowmcFlowDesc* desc, const float* params, void* image, void* stream);
 
 /* forward / inverse of the bijection on n rows: x device [n,d] -> y device [n,d], logdet device [n]
  * (MaskedCouplingRQSpline.forward / .inverse, rqSpline.py:450-488; no whitening) */

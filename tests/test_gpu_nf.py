@@ -14,6 +14,14 @@ from test_gpu_local import _make, _setup
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["fp32-cuda-cores", "tcgen05-3xtf32"])
+def flow_path(request, monkeypatch):
+    """Every test runs on both execution paths of the conditioner GEMMs (shapes outside the tensor-core path's
+    limits run the CUDA-core kernels in both)."""
+    monkeypatch.setenv("FLOWMC_FLOW_TC", "3" if request.param.startswith("tcgen05") else "0")
+    return request.param
+
 # name, target, d, n_chains, n_steps, n_batch_size, thinning, cursor, flow (L, hidden, K), gain
 CASES = [
     ("simple-iso-d2", "iso_gaussian", 2, 10, 5, 5, 1, 0, (2, [16, 16], 8), 1.0),
