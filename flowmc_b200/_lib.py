@@ -95,6 +95,7 @@ def _load() -> C.CDLL:
         "flowmc_buffer_finite_rows": (i32, [vp, i64, i64, i32, vp, vp, vp, vp]),
         "flowmc_gather_training_rows": (i32, [vp, vp, i64, i32, i32, i32, i64, i64, vp, i64, vp, vp]),
         "flowmc_data_mean_cov": (i32, [vp, i64, i32, vp, vp, vp, vp]),
+        "flowmc_debug_tc_timing": (None, [vp]),
         "flowmc_debug_tc_gemm": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
         "flowmc_nf_global_steps_workspace_bytes": (i64, [i64, i32, i32]),
         "flowmc_nf_global_steps": (i32, [C.POINTER(FlowDesc), vp, i32, vp, u32p, vp, vp, vp, vp, i64, i64, i64, i32,

@@ -128,4 +128,231 @@ __device__ __forceinline__ float rq_inverse(const RQ& q, float y, float& logdet)
   return x;
 }
 
+// Lean fused evaluation used by the flow kernels' epilogues: parameters + transform of ONE (sample, feature) with
+// only the work the selected bin needs -- 2K exponentials for the two softmaxes, one reciprocal per softmax
+// (bin size = e_i * (scale / sum) + 1e-4; the reference forms (e_i / sum) * scale, equal up to one rounding), and
+// softplus only for the two knot slopes of the selected bin (or the boundary slope in the linear tails) instead of
+// all K+1.  Same bin-selection rule and transform formulas as rq_forward / rq_inverse above.
+template <int K, bool INV>
+__device__ __forceinline__ float rq_apply(const float* raw, float rmin, float rmax, float v, float& logdet) {
+  const float scale = (rmax - rmin) - (float)K * 1e-4f;
+  const float offset = 0.5411666035652161f;
+  float mw = raw[0], mh = raw[K];
+#pragma unroll
+  for (int i = 1; i < K; ++i) {
+    mw = fmaxf(mw, raw[i]);
+    mh = fmaxf(mh, raw[K + i]);
+  }
+  float ew[K], eh[K], sw = 0.0f, sh = 0.0f;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    ew[i] = expf(raw[i] - mw);
+    eh[i] = expf(raw[K + i] - mh);
+    sw += ew[i];
+    sh += eh[i];
+  }
+  const float rw = scale / sw, rh = scale / sh;
+  // walk the knots, keeping the selected bin's corners and slope logits
+  float xk = rmin, yk = rmin;  // knot i
+  float xl = rmin, yl = rmin, xr = 0.0f, yr = 0.0f, ul = raw[2 * K], ur = raw[2 * K + 1];
+  float cx = 0.0f, cy = 0.0f;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    float xn, yn;  // knot i + 1
+    if (i < K - 1) {
+      const float bw = ew[i] * rw + 1e-4f, bh = eh[i] * rh + 1e-4f;
+      cx = (i == 0) ? bw : cx + bw;
+      cy = (i == 0) ? bh : cy + bh;
+      xn = rmin + cx;
+      yn = rmin + cy;
+    } else {
+      xn = rmax;
+      yn = rmax;
+    }
+    const float pk = INV ? yk : xk, pn = INV ? yn : xn;
+    const bool in = (i == 0) || ((v >= pk) && (v < pn));  // first bin if none matches (rqSpline.py:63-72)
+    const bool take = (i == 0) ? true : in;
+    xl = take ? xk : xl; xr = take ? xn : xr;
+    yl = take ? yk : yl; yr = take ? yn : yr;
+    if (i > 0) {
+      ul = take ? raw[2 * K + i] : ul;
+      ur = take ? raw[2 * K + i + 1] : ur;
+    }
+    xk = xn;
+    yk = yn;
+  }
+  const bool below = v <= rmin, above = v >= rmax;  // knot 0 and knot K are the range ends (both axes)
+  ul = below ? raw[2 * K] : ul;
+  ur = above ? raw[3 * K] : ur;
+  const float dl = softplus_f(ul + offset) + 1e-4f, dr = softplus_f(ur + offset) + 1e-4f;
+  const float bw = xr - xl, bh = yr - yl;
+  const float s = bh / bw;
+  const float st = dr + dl - 2.0f * s;
+  float out, z;
+  if (!INV) {
+    z = (v - xl) / bw;
+    z = fminf(fmaxf(z, 0.0f), 1.0f);
+  } else {
+    float w = (v - yl) / bh;
+    w = fminf(fmaxf(w, 0.0f), 1.0f);
+    const float c = -s * w;
+    const float b = dl - st * w;
+    const float a = s - b;
+    const float disc = b * b - 4.0f * a * c;
+    float sq = sqrtf(fmaxf(disc, 1.17549435e-38f));
+    sq = (disc > 0.0f) ? sq : 0.0f;
+    const float num = (b >= 0.0f) ? 2.0f * c : -b + sq;
+    const float den = (b >= 0.0f) ? -b - sq : 2.0f * a;
+    z = num / den;
+    z = fminf(fmaxf(z, 0.0f), 1.0f);
+  }
+  const float sq_z = z * z, z1mz = z - sq_z, omz = 1.0f - z, sq_1mz = omz * omz;
+  const float den = s + st * z1mz;
+  const float ldin = 2.0f * logf(s) + logf(dr * sq_z + 2.0f * s * z1mz + dl * sq_1mz) - 2.0f * logf(den);
+  if (!INV) {
+    out = yl + bh * (s * sq_z + dl * z1mz) / den;
+    out = below ? (v - rmin) * dl + rmin : out;
+    out = above ? (v - rmax) * dr + rmax : out;
+    logdet = below ? logf(dl) : (above ? logf(dr) : ldin);
+  } else {
+    out = bw * z + xl;
+    out = below ? (v - rmin) / dl + rmin : out;
+    out = above ? (v - rmax) / dr + rmax : out;
+    logdet = below ? -logf(dl) : (above ? -logf(dr) : -ldin);
+  }
+  return out;
+}
+
+// ---- fast variants for the tensor-core epilogue ---------------------------------------------------------------
+// The epilogue of the tcgen05 path is latency-bound: one long dependent chain per (sample, feature).  These use the
+// hardware approximations (ex2 / lg2 / rcp / sqrt .approx, 1-2 ulp, no slow-path branches) so the chain is ~2x
+// shorter; every quantity stays within ~3e-7 relative of the accurate version, far inside the 1e-5 tolerance.
+__device__ __forceinline__ float fast_exp(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+  return r;
+}
+__device__ __forceinline__ float fast_log(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 0.6931471805599453f;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_softplus(float x) {  // max(x,0) + log1p(exp(-|x|)), log1p by series when tiny
+  const float e = fast_exp(-fabsf(x));
+  const float series = e * fmaf(e, fmaf(e, 0.33333334f, -0.5f), 1.0f);
+  const float l = (e < 0.03125f) ? series : fast_log(1.0f + e);
+  return fmaxf(x, 0.0f) + l;
+}
+
+template <int K, bool INV>
+__device__ __forceinline__ float rq_apply_fast(const float* raw, float rmin, float rmax, float v, float& logdet) {
+  const float scale = (rmax - rmin) - (float)K * 1e-4f;
+  const float offset = 0.5411666035652161f;
+  float mw = raw[0], mh = raw[K];
+#pragma unroll
+  for (int i = 1; i < K; ++i) {
+    mw = fmaxf(mw, raw[i]);
+    mh = fmaxf(mh, raw[K + i]);
+  }
+  float ew[K], eh[K], sw = 0.0f, sh = 0.0f;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    ew[i] = fast_exp(raw[i] - mw);
+    eh[i] = fast_exp(raw[K + i] - mh);
+    sw += ew[i];
+    sh += eh[i];
+  }
+  const float rw = scale * fast_rcp(sw), rh = scale * fast_rcp(sh);
+  float xk = rmin, yk = rmin;
+  float xl = rmin, yl = rmin, xr = 0.0f, yr = 0.0f, ul = raw[2 * K], ur = raw[2 * K + 1];
+  float cx = 0.0f, cy = 0.0f;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    float xn, yn;
+    if (i < K - 1) {
+      cx += fmaf(ew[i], rw, 1e-4f);
+      cy += fmaf(eh[i], rh, 1e-4f);
+      xn = rmin + cx;
+      yn = rmin + cy;
+    } else {
+      xn = rmax;
+      yn = rmax;
+    }
+    const float pk = INV ? yk : xk, pn = INV ? yn : xn;
+    const bool take = (i == 0) ? true : ((v >= pk) && (v < pn));
+    xl = take ? xk : xl; xr = take ? xn : xr;
+    yl = take ? yk : yl; yr = take ? yn : yr;
+    if (i > 0) {
+      ul = take ? raw[2 * K + i] : ul;
+      ur = take ? raw[2 * K + i + 1] : ur;
+    }
+    xk = xn;
+    yk = yn;
+  }
+  const bool below = v <= rmin, above = v >= rmax;
+  ul = below ? raw[2 * K] : ul;
+  ur = above ? raw[3 * K] : ur;
+  const float dl = fast_softplus(ul + offset) + 1e-4f, dr = fast_softplus(ur + offset) + 1e-4f;
+  const float bw = xr - xl, bh = yr - yl;
+  const float rbw = fast_rcp(bw);
+  const float s = bh * rbw;
+  const float st = dr + dl - 2.0f * s;
+  float out, z;
+  if (!INV) {
+    z = (v - xl) * rbw;
+    z = fminf(fmaxf(z, 0.0f), 1.0f);
+  } else {
+    float w = (v - yl) * fast_rcp(bh);
+    w = fminf(fmaxf(w, 0.0f), 1.0f);
+    const float c = -s * w;
+    const float b = dl - st * w;
+    const float a = s - b;
+    const float disc = b * b - 4.0f * a * c;
+    float sq = fast_sqrt(fmaxf(disc, 1.17549435e-38f));
+    sq = (disc > 0.0f) ? sq : 0.0f;
+    const float num = (b >= 0.0f) ? 2.0f * c : -b + sq;
+    const float den = (b >= 0.0f) ? -b - sq : 2.0f * a;
+    z = num * fast_rcp(den);
+    z = fminf(fmaxf(z, 0.0f), 1.0f);
+  }
+  const float sq_z = z * z, z1mz = z - sq_z, omz = 1.0f - z, sq_1mz = omz * omz;
+  const float den = s + st * z1mz;
+  const float rden = fast_rcp(den);
+  const float qd = dr * sq_z + 2.0f * s * z1mz + dl * sq_1mz;
+  // 2 log s + log q - 2 log den = log(s^2 q / den^2): one logarithm
+  const float ldin = fast_log((s * s) * qd * (rden * rden));
+  if (!INV) {
+    out = yl + bh * (s * sq_z + dl * z1mz) * rden;
+    out = below ? (v - rmin) * dl + rmin : out;
+    out = above ? (v - rmax) * dr + rmax : out;
+    logdet = below ? fast_log(dl) : (above ? fast_log(dr) : ldin);
+  } else {
+    out = bw * z + xl;
+    out = below ? (v - rmin) * fast_rcp(dl) + rmin : out;
+    out = above ? (v - rmax) * fast_rcp(dr) + rmax : out;
+    logdet = below ? -fast_log(dl) : (above ? -fast_log(dr) : -ldin);
+  }
+  return out;
+}
+
+// tanh through one exponential: 1 - 2 / (1 + 2^(2 log2(e) x)) with the hardware ex2 / rcp approximations
+// (absolute error <= ~3e-7 over the whole line: the hidden activations feed dot products, where that is below the
+// fp32 rounding of the sum).  5 instructions instead of tanhf's ~30.
+__device__ __forceinline__ float tanh_ex2(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return fmaf(-2.0f, r, 1.0f);
+}
+
 }  // namespace flowmc

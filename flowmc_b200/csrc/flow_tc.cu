@@ -17,8 +17,9 @@
 //     chunk of 4 features (100 of 112 columns) is read back with tcgen05.ld (TMEM lane = sample) and softmax /
 //     cumsum / softplus / bin search / transform / log-det run in registers (flow_common.cuh), exactly the code the
 //     CUDA-core path uses.  Only the transformed half of W3 is ever loaded.
-//   * warp roles: warps 0-7 epilogue (two threads per sample row, splitting columns / features), warp 8 weight
-//     producer (one elected lane issues the bulk copies), warp 9 MMA issuer (one elected lane).
+//   * warp roles: warps 0-15 epilogue (TC_PARTS = 4 threads per sample row, splitting columns / features: four
+//     warps per scheduler hide the MUFU / TMEM latencies of the spline chains), warp 16 weight producer (one elected
+//     lane issues the bulk copies), warp 17 MMA issuer (one elected lane).
 //   TMEM map (512 columns): [0,128) A hi | [128,256) A lo | [256,384) acc slot 0 | [384,512) acc slot 1.
 #include <cstring>
 #include <string>
@@ -30,7 +31,8 @@
 namespace flowmc {
 
 constexpr int TC_M = 128;          // samples per CTA
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_PARTS = 2;        // epilogue threads per sample row (they split columns / features)
+constexpr int TC_EPI_WARPS = 4 * TC_PARTS;
 constexpr int TC_EPI = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = TC_EPI + 64;
 constexpr int TC_STAGES = 4;
@@ -57,6 +59,11 @@ struct TcProgram {
 
 static bool tc_supported(const FlowmcFlowDesc& D) {
   if (D.n_features < 2 || D.n_features > 128) return false;
+  {  // shared memory: weight stages + x tile + every layer's biases must fit one CTA
+    const size_t bytes = 2048 + (size_t)4 * 32768 + (size_t)128 * (D.n_features + 1) * 4 +
+                         (size_t)D.n_layers * ((D.n_linear - 1) * 128 + ((D.n_features + 1) / 2) * (3 * D.num_bins + 1)) * 4;
+    if (bytes > 227 * 1024) return false;
+  }
   if (D.num_bins != 4 && D.num_bins != 8 && D.num_bins != 16) return false;
   for (int i = 1; i < D.n_linear; ++i)
     if (D.dims[i] > 128 || (D.dims[i] % 16) != 0) return false;
@@ -154,12 +161,18 @@ struct TcArgs {
   const uint32_t* chain_keys;
   int64_t chain_offset;
   int n_steps, n_batch, n_sample;
+  long long* timing;  // optional diagnostics: [3][256] clock64 stamps of CTA 0 (producer, MMA issuer, epilogue thread 0)
 };
+
+#define TC_STAMP(role)                                                     \
+  do {                                                                     \
+    if (a.timing != nullptr && blockIdx.x == 0 && n_stamp < 256) a.timing[(role) * 256 + n_stamp++] = clock64(); \
+  } while (0)
 
 struct TcSmem {
   uint64_t stage_full[TC_STAGES], stage_empty[TC_STAGES], acc_full[2], acc_empty[2], a_ready;
   uint32_t tmem_base;
-  float ldpart[2][TC_M];
+  float ldpart[TC_PARTS][TC_M];
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI) : "memory"); }
@@ -175,13 +188,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
   const int d = D.n_features;
   const int xs_stride = d + 1;
   float* xs = reinterpret_cast<float*>(smem + TC_STAGES * TC_STAGE_BYTES + ((sizeof(TcSmem) + 15) & ~15));
+  // every layer's biases, staged once: per layer [hidden Linears: 128 each][spline-parameter biases of the layer's
+  // transformed features, feature-ordinal major]
+  float* sbias_all = xs + TC_M * xs_stride;
+  const int bias_stride = (D.n_linear - 1) * 128 + ((d + 1) / 2) * NP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* P = a.params;
   const int L = D.n_layers, nh = D.n_linear - 1;
   const int n_pass = (MODE == TC_NF) ? 2 : 1;
   const int64_t row0 = (int64_t)blockIdx.x * TC_M;
 
-  if (warp == 9 && lane == 0) {
+  if (warp == TC_EPI_WARPS + 1 && lane == 0) {
     for (int i = 0; i < TC_STAGES; ++i) {
       tc::mbar_init(&S->stage_full[i], 1);
       tc::mbar_init(&S->stage_empty[i], 1);
@@ -193,17 +210,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     tc::mbar_init(&S->a_ready, TC_EPI);
     tc::fence_mbar_init();
   }
-  if (warp == 8) tc::tmem_alloc<512>(&S->tmem_base);
+  if (warp == TC_EPI_WARPS) tc::tmem_alloc<512>(&S->tmem_base);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tbase = S->tmem_base;
   const uint32_t t_ahi = tbase, t_alo = tbase + 128;
 
-  if (warp == 8) {
-    // ===== weight producer =====================================================================
-    if (lane == 0) {
+  if (warp == TC_EPI_WARPS) {
+    // ===== weight producer (whole warp walks the schedule; one elected lane issues) ==============
+    {
       uint32_t s = 0, ph = 0;
+      int n_stamp = 0;
       for (int pass = 0; pass < n_pass; ++pass) {
         const bool inv = (MODE == TC_INV) || (MODE == TC_NF && pass == 0);
         for (int li = 0; li < L; ++li) {
@@ -214,25 +232,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
             const uint32_t bytes = 2u * it.npad * 128u;
             for (int kc = 0; kc < it.n_kc; ++kc) {
               tc::mbar_wait(&S->stage_empty[s], ph ^ 1);
-              tc::mbar_arrive_expect_tx(&S->stage_full[s], bytes);
-              tc::bulk_g2s(stages + (size_t)s * TC_STAGE_BYTES, lbase + it.off + (size_t)kc * bytes, bytes,
-                           &S->stage_full[s]);
+              if (tc::elect_one()) {
+                TC_STAMP(0);
+                tc::mbar_arrive_expect_tx(&S->stage_full[s], bytes);
+                tc::bulk_g2s(stages + (size_t)s * TC_STAGE_BYTES, lbase + it.off + (size_t)kc * bytes, bytes,
+                             &S->stage_full[s]);
+              }
+              __syncwarp();
               if (++s == TC_STAGES) { s = 0; ph ^= 1; }
             }
           }
         }
       }
     }
-  } else if (warp == 9) {
-    // ===== MMA issuer ==========================================================================
-    if (lane == 0) {
+  } else if (warp == TC_EPI_WARPS + 1) {
+    // ===== MMA issuer (whole warp walks the schedule; one elected lane issues) ====================
+    {
       uint32_t s = 0, ph = 0, seq = 0, a_ph = 0;
+      int n_stamp = 0;
       for (int pass = 0; pass < n_pass; ++pass) {
         const bool inv = (MODE == TC_INV) || (MODE == TC_NF && pass == 0);
         for (int li = 0; li < L; ++li) {
           const int l = inv ? L - 1 - li : li, p = l & 1;
           for (int ii = 0; ii < PR.n_items[p]; ++ii) {
-            const TcItem& it = PR.items[p][ii];
+            const TcItem it = PR.items[p][ii];
             if (it.kind == 0 || it.lin == 0) {  // a new A operand: masked x, h1, ..., h_last
               tc::mbar_wait(&S->a_ready, a_ph);
               a_ph ^= 1;
@@ -240,29 +263,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
             const uint32_t slot = seq & 1;
             tc::mbar_wait(&S->acc_empty[slot], ((seq >> 1) & 1) ^ 1);
             tc::tc_fence_after();
+            if (lane == 0) TC_STAMP(1);  // operands + accumulator slot available
             const uint32_t t_acc = tbase + 256 + slot * 128;
             const uint32_t idesc = tc::make_idesc_tf32(TC_M, it.npad);
-            uint32_t accum = 0;
+            const bool three = a.terms == 3;
             for (int kc = 0; kc < it.n_kc; ++kc) {
               tc::mbar_wait(&S->stage_full[s], ph);
               tc::tc_fence_after();
+              if (kc == 0 && lane == 0) TC_STAMP(1);  // first weight stage landed
               const uint32_t b_hi = tc::smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
-              const uint32_t b_lo = b_hi + it.npad * 128;
+              const uint64_t dhi = tc::make_b_desc(b_hi), dlo = tc::make_b_desc(b_hi + it.npad * 128);
               const int ksteps = min(4, (it.K - kc * 32 + 7) >> 3);
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t acol = kc * 32 + ks * 8;
-                const uint64_t dhi = tc::make_b_desc(b_hi + ks * 32);
-                tc::mma_tf32_ts(t_acc, t_ahi + acol, dhi, idesc, accum);
-                accum = 1;
-                if (a.terms == 3) {
-                  tc::mma_tf32_ts(t_acc, t_alo + acol, dhi, idesc, 1);
-                  tc::mma_tf32_ts(t_acc, t_ahi + acol, tc::make_b_desc(b_lo + ks * 32), idesc, 1);
+              const uint32_t acol = kc * 32;
+              if (tc::elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks < ksteps) {
+                    // +32 bytes per k-step inside the 128-byte swizzle atom = +2 in the descriptor's address field
+                    tc::mma_tf32_ts(t_acc, t_ahi + acol + ks * 8, dhi + 2 * ks, idesc, (kc | ks) != 0);
+                    if (three) {
+                      tc::mma_tf32_ts(t_acc, t_alo + acol + ks * 8, dhi + 2 * ks, idesc, 1);
+                      tc::mma_tf32_ts(t_acc, t_ahi + acol + ks * 8, dlo + 2 * ks, idesc, 1);
+                    }
+                  }
                 }
+                tc::mma_commit(&S->stage_empty[s]);
               }
-              tc::mma_commit(&S->stage_empty[s]);
+              __syncwarp();
               if (++s == TC_STAGES) { s = 0; ph ^= 1; }
             }
-            tc::mma_commit(&S->acc_full[slot]);
+            if (tc::elect_one()) tc::mma_commit(&S->acc_full[slot]);
+            __syncwarp();
+            if (lane == 0) TC_STAMP(1);  // all MMAs of the item issued
             ++seq;
           }
         }
@@ -270,7 +302,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     }
   } else {
     // ===== epilogue warps: two threads per sample row ==========================================
-    const int q = warp & 3, hf = warp >> 2;
+    const int q = warp & 3, hf = warp >> 2;  // hf: which of the row's TC_PARTS threads this is
+    auto part = [&](int n, int& lo, int& hi) {  // this thread's share [lo, hi) of n work items
+      const int per = (n + TC_PARTS - 1) / TC_PARTS;
+      lo = min(n, hf * per);
+      hi = min(n, lo + per);
+    };
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int64_t grow = row0 + row;
@@ -278,7 +315,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     float* xr = xs + row * xs_stride;
     // this thread's share of the d features (affine / operand writes / pre / post): 8-column groups
     const int g_all = (d + 7) >> 3;
-    const int g_lo = hf ? (g_all + 1) / 2 : 0, g_hi = hf ? g_all : (g_all + 1) / 2;
+    int g_lo, g_hi;
+    part(g_all, g_lo, g_hi);
     const int j_lo = g_lo * 8, j_hi = min(d, g_hi * 8);
 
     // ---- load / generate the tile ------------------------------------------------------------
@@ -314,8 +352,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
         xr[j] = v;
       }
     }
+    for (int l = 0; l < L; ++l) {  // stage the biases (visible after the first epi_bar below)
+      const float* PL = P + (int64_t)l * D.layer_stride;
+      float* sb = sbias_all + l * bias_stride;
+      const int p = l & 1, ntf = (d - p + 1) / 2;
+      for (int i = 0; i < nh; ++i)
+        for (int c = tid; c < D.dims[i + 1]; c += TC_EPI) sb[i * 128 + c] = PL[D.off_b[i] + c];
+      for (int c = tid; c < ntf * NP; c += TC_EPI) {
+        const int o = c / NP, rr = c - o * NP;
+        sb[nh * 128 + c] = PL[D.off_b[nh] + (p + 2 * o) * NP + rr];
+      }
+    }
     float ldacc = 0.0f;
     uint32_t seq = 0;
+    int n_stamp = (tid == 0) ? 0 : 256;
+    TC_STAMP(2);  // tile loaded
 
     for (int pass = 0; pass < n_pass; ++pass) {
       const bool inv = (MODE == TC_INV) || (MODE == TC_NF && pass == 0);
@@ -323,6 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
         const int l = inv ? L - 1 - li : li, p = l & 1;
         const float* PL = P + (int64_t)l * D.layer_stride;
         const float scale = PL[D.off_scale], shift = PL[D.off_shift];
+        const float* sbias = sbias_all + l * bias_stride;
         // ---- ScalarAffine (rqSpline.py:435-436) + A operand = x * mask, hi / lo ------------------
         {
           const float e = inv ? expf(-scale) : expf(scale);
@@ -348,6 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
           tc::tc_fence_before();
           tc::mbar_arrive(&S->a_ready);
           epi_bar();  // the row's other thread reads these x values in the spline stage
+          TC_STAMP(2);  // affine + operand written
         }
         for (int ii = 0; ii < PR.n_items[p]; ++ii) {
           const TcItem& it = PR.items[p][ii];
@@ -355,18 +408,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
           const uint32_t t_acc = tbase + 256 + slot * 128 + lane_base;
           tc::mbar_wait(&S->acc_full[slot], (seq >> 1) & 1);
           tc::tc_fence_after();
+          TC_STAMP(2);  // accumulator observed full
           if (it.kind == 0) {
             // ---- tanh(acc + b) -> next A operand (this thread: half of the columns) ----------------
             const int N = it.npad;               // hidden width, multiple of 16
-            const int c_lo = hf ? (N / 16 + 1) / 2 * 16 : 0, c_hi = hf ? N : (N / 16 + 1) / 2 * 16;
-            const float* bias = PL + D.off_b[it.lin];
+            int c_lo, c_hi;
+            part(N / 16, c_lo, c_hi);
+            c_lo *= 16;
+            c_hi *= 16;
+            const float* bias = sbias + it.lin * 128;
             for (int c = c_lo; c < c_hi; c += 16) {
               float v[16];
               tc::tmem_ld16(t_acc + c, v);
               tc::tmem_wait_ld();
               uint32_t hi[16], lo[16];
 #pragma unroll
-              for (int u = 0; u < 16; ++u) tc::split_tf32(tanhf(v[u] + __ldg(bias + c + u)), hi[u], lo[u]);
+              for (int u = 0; u < 16; ++u) tc::split_tf32(tanh_ex2(v[u] + bias[c + u]), hi[u], lo[u]);
               tc::tmem_st8(t_ahi + lane_base + c, hi);
               tc::tmem_st8(t_ahi + lane_base + c + 8, hi + 8);
               tc::tmem_st8(t_alo + lane_base + c, lo);
@@ -379,32 +436,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
           } else {
             // ---- spline epilogue: this thread's half of the chunk's features ------------------------
             const int nf = it.n_feat;
-            const int i_lo = hf ? (nf + 1) / 2 : 0, i_hi = hf ? nf : (nf + 1) / 2;
-            const float* bl = PL + D.off_b[nh];
-            for (int i = i_lo; i < i_hi; ++i) {
-              const int f = p + 2 * (it.lin + i);
+            int i_lo, i_hi;
+            part(nf, i_lo, i_hi);
+            const float* bl = sbias + nh * 128 + it.lin * NP;  // ordinal-major: feature i of the chunk at i * NP
+            auto load_raw = [&](int i, float* raw) {
               float v[32];
               tc::tmem_ld32(t_acc + i * NP, v);
-              tc::tmem_wait_ld();
-              float raw[NP];
-#pragma unroll
-              for (int u = 0; u < NP && u < 32; ++u) raw[u] = v[u] + __ldg(bl + f * NP + u);
               if (NP > 32) {
                 float v2[32];
                 tc::tmem_ld32(t_acc + i * NP + 32, v2);
                 tc::tmem_wait_ld();
 #pragma unroll
-                for (int u = 32; u < NP; ++u) raw[u] = v2[u - 32] + __ldg(bl + f * NP + u);
+                for (int u = 32; u < NP; ++u) raw[u] = v2[u - 32] + bl[i * NP + u];
+              } else {
+                tc::tmem_wait_ld();
               }
-              RQ qp;
-              float t;
-              rq_params<KB>(raw, D.range_min, D.range_max, qp);
-              xr[f] = inv ? rq_inverse<KB>(qp, xr[f], t) : rq_forward<KB>(qp, xr[f], t);
-              ldacc += t;
+#pragma unroll
+              for (int u = 0; u < NP && u < 32; ++u) raw[u] = v[u] + bl[i * NP + u];
+            };
+            int i = i_lo;
+            for (; i + 1 < i_hi; i += 2) {  // two independent features per iteration: ILP for the MUFU chains
+              float raw0[NP], raw1[NP], t0, t1;
+              load_raw(i, raw0);
+              load_raw(i + 1, raw1);
+              const int f0 = p + 2 * (it.lin + i), f1 = f0 + 2;
+              const float y0 = inv ? rq_apply_fast<KB, true>(raw0, D.range_min, D.range_max, xr[f0], t0)
+                                   : rq_apply_fast<KB, false>(raw0, D.range_min, D.range_max, xr[f0], t0);
+              const float y1 = inv ? rq_apply_fast<KB, true>(raw1, D.range_min, D.range_max, xr[f1], t1)
+                                   : rq_apply_fast<KB, false>(raw1, D.range_min, D.range_max, xr[f1], t1);
+              xr[f0] = y0;
+              xr[f1] = y1;
+              ldacc += t0;
+              ldacc += t1;
+            }
+            if (i < i_hi) {
+              float raw0[NP], t0;
+              load_raw(i, raw0);
+              const int f0 = p + 2 * (it.lin + i);
+              xr[f0] = inv ? rq_apply_fast<KB, true>(raw0, D.range_min, D.range_max, xr[f0], t0)
+                           : rq_apply_fast<KB, false>(raw0, D.range_min, D.range_max, xr[f0], t0);
+              ldacc += t0;
             }
             tc::tc_fence_before();
             tc::mbar_arrive(&S->acc_empty[slot]);
           }
+          TC_STAMP(2);  // item epilogue done
           ++seq;
         }
         epi_bar();  // both threads of a row see each other's feature updates
@@ -428,8 +504,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     epi_bar();
     const int post = (MODE == TC_NF) ? POST_BASE_LOGP : a.post;
     if (post == POST_BASE_LOGP) {
-      if (hf == 0 && grow < a.n)
-        a.ldout[grow] = (S->ldpart[0][row] + S->ldpart[1][row]) + base_log_prob(D, P, xr);
+      if (hf == 0 && grow < a.n) {
+        float ldsum = S->ldpart[0][row];
+#pragma unroll
+        for (int w = 1; w < TC_PARTS; ++w) ldsum += S->ldpart[w][row];
+        a.ldout[grow] = ldsum + base_log_prob(D, P, xr);
+      }
     } else {
       if (grow < a.n) {
         for (int j = j_lo; j < j_hi; ++j) {
@@ -437,21 +517,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
           if (post == POST_UNWHITEN) v = v * sqrtf(P[D.off_data_cov + (int64_t)j * d + j]) + P[D.off_data_mean + j];
           a.yout[grow * d + j] = v;
         }
-        if (hf == 0 && a.ldout != nullptr) a.ldout[grow] = S->ldpart[0][row] + S->ldpart[1][row];
+        if (hf == 0 && a.ldout != nullptr) {
+          float ldsum = S->ldpart[0][row];
+#pragma unroll
+          for (int w = 1; w < TC_PARTS; ++w) ldsum += S->ldpart[w][row];
+          a.ldout[grow] = ldsum;
+        }
       }
     }
     tc::tc_fence_before();
   }
   __syncthreads();
   tc::tc_fence_after();
-  if (warp == 8) tc::tmem_dealloc<512>(tbase);
+  if (warp == TC_EPI_WARPS) tc::tmem_dealloc<512>(tbase);
 }
 
 template <int KB, int MODE>
 static int launch_tc(const FlowmcFlowDesc& D, const TcProgram& PR, const TcArgs& a, cudaStream_t stream) {
   auto kern = flow_tc_kernel<KB, MODE>;
   const size_t bytes = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + ((sizeof(TcSmem) + 15) & ~15) +
-                       (size_t)TC_M * (D.n_features + 1) * sizeof(float);
+                       (size_t)TC_M * (D.n_features + 1) * sizeof(float) +
+                       (size_t)D.n_layers * ((D.n_linear - 1) * 128 + ((D.n_features + 1) / 2) * (3 * D.num_bins + 1)) *
+                           sizeof(float);
   static size_t configured = 0;
   if (bytes > configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
@@ -480,6 +567,8 @@ static int dispatch_tc(const FlowmcFlowDesc& D, const TcProgram& PR, const TcArg
   return FLOWMC_ERR_UNSUPPORTED;
 }
 
+static long long* g_tc_timing = nullptr;  // diagnostics hook (flowmc_debug_tc_timing)
+
 // true if the descriptor asks for (and the model shape allows) the tensor-core path
 bool flow_tc_enabled(const FlowmcFlowDesc& D) { return D.tc_image != nullptr && D.tc_terms != 0 && tc_supported(D); }
 
@@ -494,6 +583,7 @@ int flow_transform_tc(const FlowmcFlowDesc& D, bool inverse, const float* P, con
   a.params = P; a.image = static_cast<const uint8_t*>(D.tc_image); a.xin = x; a.idx = idx; a.yout = y; a.ldout = ld;
   a.n = n; a.pre = pre; a.post = post; a.terms = D.tc_terms == 1 ? 1 : 3; a.keys = keys; a.host_key = hk;
   a.rows_per_key = rpk;
+  a.timing = g_tc_timing;
   return inverse ? dispatch_tc<TC_INV>(D, PR, a, stream) : dispatch_tc<TC_FWD>(D, PR, a, stream);
 }
 
@@ -514,6 +604,10 @@ int flow_nf_propose_tc(const FlowmcFlowDesc& D, const float* P, Key subkey, cons
 }  // namespace flowmc
 
 extern "C" {
+
+// diagnostics: device buffer of 3 * 256 int64 that CTA 0 of the next tensor-core flow launches stamps with clock64()
+// (NULL switches it off).  Not thread-safe; used by scripts/tc_timeline.py only.
+void flowmc_debug_tc_timing(long long* buf) { flowmc::g_tc_timing = buf; }
 
 int64_t flowmc_flow_tc_image_bytes(const FlowmcFlowDesc* D) {
   using namespace flowmc;

@@ -215,15 +215,12 @@ __device__ __forceinline__ void flow_layers(const FlowmcFlowDesc& D, const float
             }
           }
         }
-        RQ q;
         float t;
-        rq_params<K>(r0, D.range_min, D.range_max, q);
         float* px = xs + lane * S.xs_stride + f;
-        *px = INV ? rq_inverse<K>(q, *px, t) : rq_forward<K>(q, *px, t);
+        *px = rq_apply<K, INV>(r0, D.range_min, D.range_max, *px, t);
         ldacc0 += t;
-        rq_params<K>(r1, D.range_min, D.range_max, q);
         px = xs + (lane + 32) * S.xs_stride + f;
-        *px = INV ? rq_inverse<K>(q, *px, t) : rq_forward<K>(q, *px, t);
+        *px = rq_apply<K, INV>(r1, D.range_min, D.range_max, *px, t);
         ldacc1 += t;
       }
       ldw[warp * TM + lane] = ldacc0;

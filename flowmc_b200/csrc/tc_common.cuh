@@ -18,6 +18,18 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a fully converged warp (the compiler then knows the guarded code runs on exactly one lane and keeps
+// its operands in uniform registers: no per-lane "waterfall" loop around tcgen05.mma / cp.async.bulk)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -116,11 +128,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 // x = hi + lo with hi = x rounded to nearest tf32 (10 explicit mantissa bits, cvt.rna) and lo = the exact fp32
 // remainder (|lo| <= 2^-11 |x|) again rounded to nearest tf32, so hi + lo carries x to ~2^-23.
 // a_hi b_hi + a_lo b_hi + a_hi b_lo then reproduces the fp32 product to ~2^-22 relative (the dropped a_lo b_lo).
-__device__ __forceinline__ uint32_t to_tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// Integer form of cvt.rna.tf32.f32 (round to nearest, ties away): add half a tf32 ulp to the magnitude bits and
+// clear the 13 low mantissa bits.  Two ALU-pipe instructions instead of one XU-pipe conversion -- the epilogues
+// are XU-bound (ex2 / rcp), so the split must not add to that pipe.  (Inf/NaN never occur in these operands.)
+__device__ __forceinline__ uint32_t to_tf32_rn(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = to_tf32_rn(x);
   lo = to_tf32_rn(x - __uint_as_float(hi));

@@ -1,0 +1,26 @@
+"""Pipeline timeline of CTA 0 of the tensor-core flow kernel (clock64 stamps) for one log_prob launch."""
+import sys
+sys.path.insert(0, "/root/repo")
+import torch
+from flowmc_b200 import random as frandom
+from flowmc_b200._lib import lib
+from flowmc_b200.resource.model.nf_model.rqSpline import MaskedCouplingRQSpline
+
+d, L = (32, 10) if (len(sys.argv) < 2 or sys.argv[1] == "c4") else (64, 8)
+terms = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+m = MaskedCouplingRQSpline(d, L, [128, 128], 8, frandom.PRNGKey(1))
+m.tc_terms = terms
+x = frandom.normal(frandom.PRNGKey(2), (148 * 128, d))
+m.log_prob(x)
+buf = torch.zeros(3 * 256, dtype=torch.int64, device="cuda")
+lib.flowmc_debug_tc_timing(buf.data_ptr())
+m.log_prob(x)
+torch.cuda.synchronize()
+lib.flowmc_debug_tc_timing(None)
+t = buf.cpu().numpy().reshape(3, 256)
+t0 = t[t > 0].min()
+for role, name in enumerate(("producer (stage slot free -> copy issued)", "mma (ready | first stage | issued)",
+                             "epilogue thread 0")):
+    v = t[role][t[role] > 0] - t0
+    print(name, len(v))
+    print(" ", " ".join(str(int(c)) for c in v[:80]))
