@@ -161,6 +161,10 @@ struct TcArgs {
   const uint32_t* chain_keys;
   int64_t chain_offset;
   int n_steps, n_batch, n_sample;
+  // training forward (MODE FWD): optional activation dump for the backward pass (flow_train.cu)
+  float* save_x;      // [L + 1][n][d]            every layer's input, then the final latent
+  float* save_h;      // [L][n_hidden][128][n]    hidden activations, column-major over samples
+  float* save_theta;  // [L][ceil(d/2) * NP][n]   spline parameters (bias included) of the transformed features
   long long* timing;  // optional diagnostics: [3][256] clock64 stamps of CTA 0 (producer, MMA issuer, epilogue thread 0)
 };
 
@@ -375,6 +379,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
         const float* PL = P + (int64_t)l * D.layer_stride;
         const float scale = PL[D.off_scale], shift = PL[D.off_shift];
         const float* sbias = sbias_all + l * bias_stride;
+        if (MODE == TC_FWD && a.save_x != nullptr && grow < a.n)
+          for (int j = j_lo; j < j_hi; ++j) a.save_x[((int64_t)l * a.n + grow) * d + j] = xr[j];
         // ---- ScalarAffine (rqSpline.py:435-436) + A operand = x * mask, hi / lo ------------------
         {
           const float e = inv ? expf(-scale) : expf(scale);
@@ -423,7 +429,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
               tc::tmem_wait_ld();
               uint32_t hi[16], lo[16];
 #pragma unroll
-              for (int u = 0; u < 16; ++u) tc::split_tf32(tanh_ex2(v[u] + bias[c + u]), hi[u], lo[u]);
+              for (int u = 0; u < 16; ++u) {
+                const float hv = tanh_ex2(v[u] + bias[c + u]);
+                tc::split_tf32(hv, hi[u], lo[u]);
+                if (MODE == TC_FWD && a.save_h != nullptr && grow < a.n)
+                  a.save_h[((int64_t)(l * nh + it.lin) * 128 + c + u) * a.n + grow] = hv;
+              }
               tc::tmem_st8(t_ahi + lane_base + c, hi);
               tc::tmem_st8(t_ahi + lane_base + c + 8, hi + 8);
               tc::tmem_st8(t_alo + lane_base + c, lo);
@@ -453,6 +464,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
               }
 #pragma unroll
               for (int u = 0; u < NP && u < 32; ++u) raw[u] = v[u] + bl[i * NP + u];
+              if (MODE == TC_FWD && a.save_theta != nullptr && grow < a.n) {
+                float* dst = a.save_theta + ((int64_t)l * ((d + 1) / 2) + it.lin + i) * NP * a.n + grow;
+#pragma unroll
+                for (int u = 0; u < NP; ++u) dst[(int64_t)u * a.n] = raw[u];
+              }
             };
             int i = i_lo;
             for (; i + 1 < i_hi; i += 2) {  // two independent features per iteration: ILP for the MUFU chains
@@ -500,6 +516,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     }
 
     // ---- epilogue of the tile ------------------------------------------------------------------
+    if (MODE == TC_FWD && a.save_x != nullptr && grow < a.n)
+      for (int j = j_lo; j < j_hi; ++j) a.save_x[((int64_t)L * a.n + grow) * d + j] = xr[j];
     S->ldpart[hf][row] = ldacc;
     epi_bar();
     const int post = (MODE == TC_NF) ? POST_BASE_LOGP : a.post;
@@ -574,7 +592,7 @@ bool flow_tc_enabled(const FlowmcFlowDesc& D) { return D.tc_image != nullptr && 
 
 int flow_transform_tc(const FlowmcFlowDesc& D, bool inverse, const float* P, const float* x, int64_t n, float* y,
                       float* ld, int pre, int post, const uint32_t* keys, Key hk, int64_t rpk, cudaStream_t stream,
-                      const int32_t* idx) {
+                      const int32_t* idx, float* save_x, float* save_h, float* save_theta) {
   if (n <= 0) return FLOWMC_OK;
   TcProgram PR;
   if (int rc = tc_build_program(D, &PR)) return rc;
@@ -583,6 +601,7 @@ int flow_transform_tc(const FlowmcFlowDesc& D, bool inverse, const float* P, con
   a.params = P; a.image = static_cast<const uint8_t*>(D.tc_image); a.xin = x; a.idx = idx; a.yout = y; a.ldout = ld;
   a.n = n; a.pre = pre; a.post = post; a.terms = D.tc_terms == 1 ? 1 : 3; a.keys = keys; a.host_key = hk;
   a.rows_per_key = rpk;
+  a.save_x = save_x; a.save_h = save_h; a.save_theta = save_theta;
   a.timing = g_tc_timing;
   return inverse ? dispatch_tc<TC_INV>(D, PR, a, stream) : dispatch_tc<TC_FWD>(D, PR, a, stream);
 }

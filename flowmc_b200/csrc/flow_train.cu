@@ -23,6 +23,7 @@
 // clip + Adam moments + bias correction + decoupled weight decay + learning rate in one pass over the
 // flat parameter / moment vectors.
 #include <cmath>
+#include <cstdlib>
 #include <string>
 
 #include "flow_tile.cuh"
@@ -280,7 +281,9 @@ __global__ void __launch_bounds__(NT) flow_backward_kernel(const FlowmcFlowDesc 
                                                            const float* __restrict__ layer_inputs,
                                                            const float* __restrict__ logp, int64_t n, float inv_n,
                                                            int fc, float* __restrict__ grad,
-                                                           float* __restrict__ loss) {
+                                                           float* __restrict__ loss,
+                                                           const float* __restrict__ saved_h,
+                                                           const float* __restrict__ saved_theta) {
   extern __shared__ __align__(16) float smem[];
   constexpr int NP = 3 * K + 1;
   constexpr int NP4 = (NP + 3) & ~3;
@@ -331,7 +334,19 @@ __global__ void __launch_bounds__(NT) flow_backward_kernel(const FlowmcFlowDesc 
       xa[s * S.xs_stride + j] = (layer_inputs[((int64_t)l * n + r) * d + j] + shift) * e;
     }
     __syncthreads();
-    {
+    if (saved_h != nullptr) {
+      // activations kept by the tensor-core forward pass ([L][n_hidden][128][n], sample-contiguous)
+      for (int i = 0; i < n_lin - 1; ++i) {
+        float* out_s = smem + S.h[i];
+        const int N = D.dims[i + 1];
+        const float* src = saved_h + ((int64_t)(l * (n_lin - 1) + i) * 128) * n + row0;
+        for (int e = tid; e < N * TM; e += NT) {
+          const int k = e / TM, s = e - k * TM;
+          out_s[s * S.a_stride + k] = (s < n_valid) ? src[(int64_t)k * n + s] : 0.0f;
+        }
+      }
+      __syncthreads();
+    } else {
       const float* in_s = xa;
       int in_stride = S.xs_stride;
       for (int i = 0; i < n_lin - 1; ++i) {
@@ -362,9 +377,18 @@ __global__ void __launch_bounds__(NT) flow_backward_kernel(const FlowmcFlowDesc 
         const float* h1 = hl + (lane + 32) * S.a_stride;
         float r0[NP], r1[NP];
         const float* wbase = Wl + (int64_t)f * NP * H;
+        if (saved_theta != nullptr) {
+          // spline parameters kept by the forward pass ([L][ceil(d/2) * NP][n], sample-contiguous): no GEMM
+          const float* src = saved_theta + ((int64_t)l * ((d + 1) / 2) + (c0 + warp)) * NP * n + row0;
+          const bool v0 = lane < n_valid, v1 = lane + 32 < n_valid;
 #pragma unroll
-        for (int r = 0; r < NP; ++r) r0[r] = r1[r] = __ldg(bl + f * NP + r);
-        if ((H & 3) == 0) {
+          for (int r = 0; r < NP; ++r) {
+            r0[r] = v0 ? src[(int64_t)r * n + lane] : 0.0f;
+            r1[r] = v1 ? src[(int64_t)r * n + lane + 32] : 0.0f;
+          }
+        } else if ((H & 3) == 0) {
+#pragma unroll
+          for (int r = 0; r < NP; ++r) r0[r] = r1[r] = __ldg(bl + f * NP + r);
           for (int k = 0; k < H; k += 4) {
             const float4 u0 = *reinterpret_cast<const float4*>(h0 + k);
             const float4 u1 = *reinterpret_cast<const float4*>(h1 + k);
@@ -378,6 +402,8 @@ __global__ void __launch_bounds__(NT) flow_backward_kernel(const FlowmcFlowDesc 
             }
           }
         } else {
+#pragma unroll
+          for (int r = 0; r < NP; ++r) r0[r] = r1[r] = __ldg(bl + f * NP + r);
           for (int k = 0; k < H; ++k) {
             const float u0 = h0[k], u1 = h1[k];
 #pragma unroll
@@ -552,7 +578,8 @@ __global__ void __launch_bounds__(NT) flow_backward_kernel(const FlowmcFlowDesc 
 
 template <int K>
 static int launch_backward(const FlowmcFlowDesc& D, const float* P, const float* layer_inputs, const float* logp,
-                           int64_t n, float inv_n, float* grad, float* loss, cudaStream_t stream) {
+                           int64_t n, float inv_n, float* grad, float* loss, const float* saved_h,
+                           const float* saved_theta, cudaStream_t stream) {
   auto kern = flow_backward_kernel<K>;
   static int max_smem = 0;
   if (max_smem == 0) {
@@ -575,7 +602,8 @@ static int launch_backward(const FlowmcFlowDesc& D, const float* P, const float*
     }
     configured = bytes;
   }
-  kern<<<(unsigned)((n + TM - 1) / TM), NT, bytes, stream>>>(D, P, layer_inputs, logp, n, inv_n, fc, grad, loss);
+  kern<<<(unsigned)((n + TM - 1) / TM), NT, bytes, stream>>>(D, P, layer_inputs, logp, n, inv_n, fc, grad, loss,
+                                                             saved_h, saved_theta);
   flowmc_count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -644,9 +672,15 @@ __global__ void __launch_bounds__(256) clip_adamw_kernel(float* __restrict__ p, 
 
 extern "C" {
 
+static int64_t pad4i(int64_t v) { return (v + 3) & ~(int64_t)3; }
+
 int64_t flowmc_flow_loss_grad_workspace_bytes(const FlowmcFlowDesc* D, int64_t n) {
   if (!D || n <= 0) return 0;
-  return 4 * ((int64_t)(D->n_layers + 1) * n * D->n_features + ((n + 3) & ~(int64_t)3));
+  const int64_t NP = 3 * D->num_bins + 1;
+  // layer inputs + final latent, log-probs, and (tensor-core forward) the hidden activations and spline parameters
+  return 4 * (pad4i((int64_t)(D->n_layers + 1) * n * D->n_features) + pad4i(n) +
+              pad4i((int64_t)D->n_layers * (D->n_linear - 1) * 128 * n) +
+              pad4i((int64_t)D->n_layers * ((D->n_features + 1) / 2) * NP * n));
 }
 
 int flowmc_flow_loss_grad(const FlowmcFlowDesc* D, const float* params, const float* x, const int32_t* idx,
@@ -666,15 +700,44 @@ int flowmc_flow_loss_grad(const FlowmcFlowDesc* D, const float* params, const fl
   cudaMemsetAsync(grad, 0, (size_t)D->n_params * sizeof(float), stream);
   cudaMemsetAsync(loss, 0, sizeof(float), stream);
   if (n == 0) return FLOWMC_OK;
+  const int64_t NP = 3 * D->num_bins + 1;
   float* layer_inputs = static_cast<float*>(workspace);
-  float* logp = layer_inputs + (int64_t)(D->n_layers + 1) * n * D->n_features;
-  if (int rc = flow_transform(*D, false, params, x, n, nullptr, logp, layer_inputs, PRE_WHITEN, POST_BASE_LOGP,
-                              nullptr, Key{0, 0}, 1, stream, idx))
-    return rc;
+  float* logp = layer_inputs + pad4i((int64_t)(D->n_layers + 1) * n * D->n_features);
+  float* save_h = logp + pad4i(n);
+  float* save_theta = save_h + pad4i((int64_t)D->n_layers * (D->n_linear - 1) * 128 * n);
+  (void)NP;
+  const bool tcf = flow_tc_enabled(*D);
+  // The tensor-core forward can also hand its hidden activations and spline parameters to the backward kernel
+  // (no conditioner recompute: -27 % instructions).  Measured on B200 (profiles/r01_flow_backward_c4_ncu.txt) the
+  // CUDA-core backward is bound by the L2 latency of its weight loads, not by instruction count, and the extra
+  // 430 MB/step of activation traffic makes it 12 % SLOWER -- so recompute stays the default; the hand-off is kept
+  // (FLOWMC_BWD_SAVED=1, covered by tests) as the interface a tcgen05 backward will use.
+  static const bool use_saved = [] {
+    const char* e = std::getenv("FLOWMC_BWD_SAVED");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (tcf) {
+    if (!use_saved) {
+      save_h = nullptr;
+      save_theta = nullptr;
+    }
+    if (int rc = flow_transform_tc(*D, false, params, x, n, nullptr, logp, PRE_WHITEN, POST_BASE_LOGP, nullptr,
+                                   Key{0, 0}, 1, stream, idx, layer_inputs, save_h, save_theta))
+      return rc;
+  } else {
+    if (int rc = flow_transform(*D, false, params, x, n, nullptr, logp, layer_inputs, PRE_WHITEN, POST_BASE_LOGP,
+                                nullptr, Key{0, 0}, 1, stream, idx))
+      return rc;
+    save_h = nullptr;
+    save_theta = nullptr;
+  }
   switch (D->num_bins) {
-    case 4: return launch_backward<4>(*D, params, layer_inputs, logp, n, inv_n_total, grad, loss, stream);
-    case 8: return launch_backward<8>(*D, params, layer_inputs, logp, n, inv_n_total, grad, loss, stream);
-    case 16: return launch_backward<16>(*D, params, layer_inputs, logp, n, inv_n_total, grad, loss, stream);
+    case 4:
+      return launch_backward<4>(*D, params, layer_inputs, logp, n, inv_n_total, grad, loss, save_h, save_theta, stream);
+    case 8:
+      return launch_backward<8>(*D, params, layer_inputs, logp, n, inv_n_total, grad, loss, save_h, save_theta, stream);
+    case 16:
+      return launch_backward<16>(*D, params, layer_inputs, logp, n, inv_n_total, grad, loss, save_h, save_theta, stream);
     default:
       flowmc_set_error("flow: num_bins must be 4, 8 or 16");
       return FLOWMC_ERR_UNSUPPORTED;

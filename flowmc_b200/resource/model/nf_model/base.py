@@ -86,8 +86,8 @@ class NFModel(Resource):
         x = x.contiguous()
         n = int(idx.numel()) if idx is not None else int(x.shape[0])
         sc = scratch or _TrainScratch(self, 0, n)
+        self.prepare()     # refresh the tensor-core weight image: params change every step
         with torch.cuda.device(x.device):
-            # (training's forward pass stores every layer's input: it runs on the fp32 CUDA-core kernels)
             check(lib.flowmc_flow_loss_grad(C.byref(self.desc), self.params.data_ptr(), x.data_ptr(),
                                             idx.data_ptr() if idx is not None else None, n,
                                             1.0 / float(n_global or n), sc.grad.data_ptr(), sc.loss.data_ptr(),

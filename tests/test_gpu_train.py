@@ -14,6 +14,14 @@ from parity import assert_close
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["fp32-cuda-cores", "tcgen05-3xtf32"])
+def flow_path(request, monkeypatch):
+    """Both execution paths of the training forward pass (the tensor-core one also hands its activations to the
+    backward kernel instead of having them recomputed)."""
+    monkeypatch.setenv("FLOWMC_FLOW_TC", "3" if request.param.startswith("tcgen05") else "0")
+    return request.param
+
 GRAD_CASES = [
     # d, layers, hidden, bins, n
     (5, 4, [32, 32], 8, 100),
