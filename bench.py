@@ -117,6 +117,83 @@ def cpu_reference_rate(target_seconds: float = 12.0):
     return n * steps / dt, cref.num_threads(), steps, dt
 
 
+def flow_extras(dev):
+    """Short device-timed measurements of the flow kernels at the BASELINE.json shapes (C4 training batch,
+    C5 global steps); reported under "extra" next to the headline local-step metric."""
+    import torch
+    from flowmc_b200 import random as frandom, targets as T
+    from flowmc_b200.resource.buffers import Buffer
+    from flowmc_b200.resource.kernel.NF_proposal import NFProposal
+    from flowmc_b200.resource.logPDF import LogPDF
+    from flowmc_b200.resource.model.nf_model.rqSpline import MaskedCouplingRQSpline
+    from flowmc_b200.resource.optimizer import Optimizer
+    from flowmc_b200.resource.states import State
+    from flowmc_b200.strategy.take_steps import TakeGroupSteps
+
+    def timed(fn, iters=5, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    def useful_flops(d, L, h, K):   # SURVEY 8(d): transformed half of W3, conditioning half of W1
+        return 2 * L * ((d // 2) * h + h * h + h * (d // 2) * (3 * K + 1))
+
+    out = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        bf16 = float(peaks["bf16_tflops"])
+    except Exception:
+        bf16 = 1590.0
+    tf32_peak = bf16 / 2.0      # dense TF32 = half the bf16 rate on this part (nominal 1.1 vs 2.25 PFLOP/s)
+    # C4 flow: 32-D, 10 layers, [128,128], 8 bins
+    m = MaskedCouplingRQSpline(32, 10, [128, 128], 8, frandom.PRNGKey(1), device=dev)
+    n = 148 * 128 * 4
+    x = frandom.normal(frandom.PRNGKey(2), (n, 32), device=dev)
+    ms = timed(lambda: m.log_prob(x))
+    fl = useful_flops(32, 10, 128, 8)
+    out["flow_log_prob_c4"] = {
+        "samples_per_s": n / ms * 1e3, "useful_tflops": fl * n / ms / 1e9, "path": f"tcgen05 {m.desc.tc_terms}xTF32"
+        if m.desc.tc_terms else "fp32 CUDA cores",
+        "tensor_issued_frac_of_tf32_peak": (3 if m.desc.tc_terms == 3 else 1) * 1.12 * 1.29 * fl * n / ms / 1e9 / tf32_peak,
+        "note": "issued = 3 MMA terms x 112/100 column padding x dense W1 (masked inputs are multiplied as zeros); "
+                "TF32 peak taken as bf16_tflops / 2 from MEASURED_PEAKS.json; ncu sm__pipe_tensor_cycles_active for "
+                "this kernel is in profiles/r01_flow_tc_c4_logprob_ncu.txt"}
+    opt = Optimizer(m, 1e-3)
+    bs = 16384
+    idx = torch.arange(bs, dtype=torch.int32, device=dev)
+    ms = timed(lambda: m.train_step(x, opt.optim, opt.optim_state, idx))
+    out["flow_train_c4"] = {"samples_per_s": bs / ms * 1e3, "batch": bs, "ms_per_step": ms,
+                            "useful_tflops": 3 * fl * bs / ms / 1e9,
+                            "note": "forward (tcgen05) + hand-written backward (fp32 CUDA cores) + fused clip/AdamW"}
+    # C5 global steps: 64-D, 8 layers, 65536 chains x 10 proposals
+    d, n_chains, n_steps = 64, 65536, 10
+    m5 = MaskedCouplingRQSpline(d, 8, [128, 128], 8, frandom.PRNGKey(1), device=dev)
+    mu = np.zeros((8, d), np.float32)
+    for i in range(8):
+        mu[i, i] = 3.0 if i % 2 == 0 else -3.0
+    res = {"p": Buffer("p", (n_chains, n_steps, d), 1, device=dev), "l": Buffer("l", (n_chains, n_steps), 1, device=dev),
+           "a": Buffer("a", (n_chains, n_steps), 1, device=dev), "s": State({"p": "p", "l": "l", "a": "a"}, "s"),
+           "k": NFProposal(m5), "logpdf": LogPDF(T.gaussian_mixture(mu, 1.0), n_dims=d)}
+    x0 = frandom.normal(frandom.PRNGKey(5), (n_chains, d), device=dev)
+    strat = TakeGroupSteps("logpdf", "k", "s", ["p", "l", "a"], n_steps)
+
+    def run():
+        strat.set_current_position(0)
+        strat(frandom.PRNGKey(9), res, x0, None)
+    ms = timed(run)
+    out["nf_global_steps_c5"] = {"chain_steps_per_s": n_chains * n_steps / ms * 1e3, "ms_per_call": ms,
+                                 "useful_tflops": 2 * useful_flops(d, 8, 128, 8) * n_chains * n_steps / ms / 1e9,
+                                 "note": "65536 chains x 10 NFProposal steps: flow inverse + forward, target, accept scan"}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -273,6 +350,10 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    try:
+        extras = flow_extras(dev)
+    except Exception as ex:  # the headline line must still be printed
+        extras = {"error": repr(ex)}
     peak, peak_src = measured_peak()
     avg_kernel_ms = float(np.mean(kernel_ms))
     achieved = n * N_LOCAL_STEPS * BYTES_PER_CHAIN_STEP / (avg_kernel_ms * 1e-3) / 1e9
@@ -304,6 +385,7 @@ def run_ours(args):
                      "note": "bit-exact threefry2x32 makes this kernel instruction-issue bound, see DESIGN.md"},
         "cpu_baseline": {"value": cpu_rate, "unit": "chain-steps/s", "cores": cpu_threads, "kind": "port",
                          "sample": f"{n} chains x {cpu_steps} MALA steps ({cpu_dt:.1f} s), same target and seeds"},
+        "extra": extras,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
