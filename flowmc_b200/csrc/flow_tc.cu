@@ -24,19 +24,13 @@
 #include <cstring>
 #include <string>
 
+#include "flow_tc.cuh"
 #include "flow_tile.cuh"
 #include "registry.h"
-#include "tc_common.cuh"
 
 namespace flowmc {
 
-constexpr int TC_M = 128;          // samples per CTA
-constexpr int TC_PARTS = 2;        // epilogue threads per sample row (they split columns / features)
-constexpr int TC_EPI_WARPS = 4 * TC_PARTS;
-constexpr int TC_EPI = TC_EPI_WARPS * 32;
-constexpr int TC_THREADS = TC_EPI + 64;
 constexpr int TC_STAGES = 4;
-constexpr int TC_STAGE_BYTES = 2 * 128 * 128;  // hi + lo images of up to 128 rows x 128 B
 constexpr int TC_MAX_ITEMS = 40;
 
 enum : int { TC_FWD = 0, TC_INV = 1, TC_NF = 2 };
@@ -57,7 +51,7 @@ struct TcProgram {
   TcItem items[2][TC_MAX_ITEMS];
 };
 
-static bool tc_supported(const FlowmcFlowDesc& D) {
+bool tc_supported(const FlowmcFlowDesc& D) {
   if (D.n_features < 2 || D.n_features > 128) return false;
   {  // shared memory: weight stages + x tile + every layer's biases must fit one CTA
     const size_t bytes = 2048 + (size_t)4 * 32768 + (size_t)128 * (D.n_features + 1) * 4 +
@@ -165,6 +159,8 @@ struct TcArgs {
   float* save_x;      // [L + 1][n][d]            every layer's input, then the final latent
   float* save_h;      // [L][n_hidden][128][n]    hidden activations, column-major over samples
   float* save_theta;  // [L][ceil(d/2) * NP][n]   spline parameters (bias included) of the transformed features
+  uint8_t* act_img;   // per (tile, layer): conditioner input and hidden activations as packed B stages (K = the
+                      // tile's 128 rows) for the tensor-core weight-gradient GEMMs (flow_tc.cuh: tc_act_*)
   long long* timing;  // optional diagnostics: [3][256] clock64 stamps of CTA 0 (producer, MMA issuer, epilogue thread 0)
 };
 
@@ -179,7 +175,6 @@ struct TcSmem {
   float ldpart[TC_PARTS][TC_M];
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI) : "memory"); }
 
 template <int KB, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlowDesc D, const TcProgram PR,
@@ -400,6 +395,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
             }
             tc::tmem_st8(t_ahi + lane_base + g * 8, hi);
             tc::tmem_st8(t_alo + lane_base + g * 8, lo);
+            if (MODE == TC_FWD && a.act_img != nullptr) {
+              const int npx = tc_pad16(d);
+              uint32_t* img = reinterpret_cast<uint32_t*>(a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) +
+                                                          (size_t)q * 2 * npx * 128);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int o = tc::packed_b_offset(g * 8 + u, lane) >> 2;
+                img[o] = hi[u];
+                img[npx * 32 + o] = lo[u];
+              }
+            }
           }
           if (hf == 0) ldacc += inv ? -(float)d * scale : (float)d * scale;
           tc::tmem_wait_st();
@@ -434,6 +440,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
                 tc::split_tf32(hv, hi[u], lo[u]);
                 if (MODE == TC_FWD && a.save_h != nullptr && grow < a.n)
                   a.save_h[((int64_t)(l * nh + it.lin) * 128 + c + u) * a.n + grow] = hv;
+              }
+              if (MODE == TC_FWD && a.act_img != nullptr) {
+                uint32_t* img = reinterpret_cast<uint32_t*>(a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) +
+                                                            tc_act_item_off(D, it.lin + 1) + (size_t)q * 2 * N * 128);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                  const int o = tc::packed_b_offset(c + u, lane) >> 2;
+                  img[o] = hi[u];
+                  img[N * 32 + o] = lo[u];
+                }
               }
               tc::tmem_st8(t_ahi + lane_base + c, hi);
               tc::tmem_st8(t_ahi + lane_base + c + 8, hi + 8);
@@ -592,7 +608,7 @@ bool flow_tc_enabled(const FlowmcFlowDesc& D) { return D.tc_image != nullptr && 
 
 int flow_transform_tc(const FlowmcFlowDesc& D, bool inverse, const float* P, const float* x, int64_t n, float* y,
                       float* ld, int pre, int post, const uint32_t* keys, Key hk, int64_t rpk, cudaStream_t stream,
-                      const int32_t* idx, float* save_x, float* save_h, float* save_theta) {
+                      const int32_t* idx, float* save_x, float* save_h, float* save_theta, uint8_t* act_img) {
   if (n <= 0) return FLOWMC_OK;
   TcProgram PR;
   if (int rc = tc_build_program(D, &PR)) return rc;
@@ -601,7 +617,7 @@ int flow_transform_tc(const FlowmcFlowDesc& D, bool inverse, const float* P, con
   a.params = P; a.image = static_cast<const uint8_t*>(D.tc_image); a.xin = x; a.idx = idx; a.yout = y; a.ldout = ld;
   a.n = n; a.pre = pre; a.post = post; a.terms = D.tc_terms == 1 ? 1 : 3; a.keys = keys; a.host_key = hk;
   a.rows_per_key = rpk;
-  a.save_x = save_x; a.save_h = save_h; a.save_theta = save_theta;
+  a.save_x = save_x; a.save_h = save_h; a.save_theta = save_theta; a.act_img = act_img;
   a.timing = g_tc_timing;
   return inverse ? dispatch_tc<TC_INV>(D, PR, a, stream) : dispatch_tc<TC_FWD>(D, PR, a, stream);
 }

@@ -62,7 +62,7 @@ bool flow_tc_enabled(const FlowmcFlowDesc& D);
 int flow_transform_tc(const FlowmcFlowDesc& D, bool inverse, const float* P, const float* x, int64_t n, float* y,
                       float* ld, int pre, int post, const uint32_t* keys, Key hk, int64_t rpk, cudaStream_t stream,
                       const int32_t* idx, float* save_x = nullptr, float* save_h = nullptr,
-                      float* save_theta = nullptr);
+                      float* save_theta = nullptr, uint8_t* act_img = nullptr);
 int flow_nf_propose_tc(const FlowmcFlowDesc& D, const float* P, Key subkey, const uint32_t* chain_keys,
                        int64_t chain_offset, int64_t n_chains, int n_steps, int n_batch, int n_sample, float* props,
                        float* lp_nf, cudaStream_t stream);

@@ -27,6 +27,7 @@
 #include <string>
 
 #include "flow_tile.cuh"
+#include "flow_train.cuh"
 #include "registry.h"
 
 namespace flowmc {
@@ -53,131 +54,6 @@ __host__ __device__ inline TrainSmem train_smem_layout(const FlowmcFlowDesc& D, 
   s.red = o; o += 2 * NW;
   s.total = o;
   return s;
-}
-
-__device__ __forceinline__ float sigmoid_f(float t) { return 1.0f / (1.0f + expf(-t)); }
-
-// Spline forward + reverse pass for one (sample, feature).
-//   raw[3K+1]  conditioner output;  x  input;  Gy = dL/dy,  Gld = dL/dlogdet
-//   -> gx = dL/dx (direct path),  draw[3K+1] = dL/draw.
-// Same arithmetic as rq_params / rq_forward for everything that decides the bin.
-template <int K>
-__device__ __forceinline__ void rq_backward(const float* raw, float rmin, float rmax, float x, float Gy, float Gld,
-                                            float& gx, float* draw) {
-  const float size = rmax - rmin;
-  const float scale = size - (float)K * 1e-4f;
-  const float offset = 0.5411666035652161f;
-  float mw = raw[0], mh = raw[K];
-#pragma unroll
-  for (int i = 1; i < K; ++i) {
-    mw = fmaxf(mw, raw[i]);
-    mh = fmaxf(mh, raw[K + i]);
-  }
-  float pw[K], ph[K], sw = 0.0f, sh = 0.0f;
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    pw[i] = expf(raw[i] - mw);
-    ph[i] = expf(raw[K + i] - mh);
-    sw += pw[i];
-    sh += ph[i];
-  }
-  float xp[K + 1], yp[K + 1];
-  xp[0] = rmin;
-  yp[0] = rmin;
-  float cx = 0.0f, cy = 0.0f;
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    pw[i] = pw[i] / sw;
-    ph[i] = ph[i] / sh;
-    if (i < K - 1) {
-      const float bw = pw[i] * scale + 1e-4f;
-      const float bh = ph[i] * scale + 1e-4f;
-      cx = (i == 0) ? bw : cx + bw;
-      cy = (i == 0) ? bh : cy + bh;
-      xp[i + 1] = rmin + cx;
-      yp[i + 1] = rmin + cy;
-    }
-  }
-  xp[K] = rmax;
-  yp[K] = rmax;
-  // bin select (rqSpline.py:63-72: first bin if none)
-  int kb = 0;
-  float xl = xp[0], xr = xp[1], yl = yp[0], yr = yp[1], ul = raw[2 * K], ur = raw[2 * K + 1];
-#pragma unroll
-  for (int i = 1; i < K; ++i) {
-    const bool in = (x >= xp[i]) && (x < xp[i + 1]);
-    kb = in ? i : kb;
-    xl = in ? xp[i] : xl; xr = in ? xp[i + 1] : xr;
-    yl = in ? yp[i] : yl; yr = in ? yp[i + 1] : yr;
-    ul = in ? raw[2 * K + i] : ul; ur = in ? raw[2 * K + i + 1] : ur;
-  }
-  const bool below = x <= xp[0], above = x >= xp[K];
-  if (below) { ul = raw[2 * K]; }
-  if (above) { ur = raw[3 * K]; }
-  const float dl = softplus_f(ul + offset) + 1e-4f, dr = softplus_f(ur + offset) + 1e-4f;
-
-  const float bw = xr - xl, bh = yr - yl;
-  const float s = bh / bw;
-  float z = (x - xl) / bw;
-  z = fminf(fmaxf(z, 0.0f), 1.0f);
-  const float sq_z = z * z, z1mz = z - sq_z, omz = 1.0f - z, sq_1mz = omz * omz;
-  const float st = dr + dl - 2.0f * s;
-  const float nu = s * sq_z + dl * z1mz;  // num = bh * nu
-  const float den = s + st * z1mz;
-  const float q = dr * sq_z + 2.0f * s * z1mz + dl * sq_1mz;
-  // ---- reverse pass, in-range branch --------------------------------------------------------
-  const float a_num = Gy / den;
-  float a_den = -Gy * (bh * nu) / (den * den) - 2.0f * Gld / den;
-  const float a_q = Gld / q;
-  float a_s = 2.0f * Gld / s + a_q * 2.0f * z1mz + a_den * (1.0f - 2.0f * z1mz) + a_num * bh * sq_z;
-  float a_dr = a_q * sq_z + a_den * z1mz;
-  float a_dl = a_q * sq_1mz + a_den * z1mz + a_num * bh * z1mz;
-  const float a_z = a_q * (2.0f * dr * z + 2.0f * s * (1.0f - 2.0f * z) - 2.0f * dl * omz) +
-                    a_den * st * (1.0f - 2.0f * z) + a_num * bh * (2.0f * s * z + dl * (1.0f - 2.0f * z));
-  float a_bh = a_num * nu + a_s / bw;
-  float a_bw = -a_z * z / bw - a_s * s / bw;
-  gx = a_z / bw;
-  float a_xl = -a_z / bw - a_bw;
-  float a_xr = a_bw;
-  float a_yl = Gy - a_bh;
-  float a_yr = a_bh;
-  // ---- linear tails (rqSpline.py:118-127): y = (x - x_e) d_e + y_e, logdet = log d_e ------------
-  if (below || above) {
-    const float de = below ? dl : dr;
-    const float xe = below ? xp[0] : xp[K];
-    gx = Gy * de;
-    const float a_de = Gy * (x - xe) + Gld / de;
-    a_dl = below ? a_de : 0.0f;
-    a_dr = above ? a_de : 0.0f;
-    a_xl = a_xr = a_yl = a_yr = 0.0f;
-  }
-  const int kl = below ? 0 : (above ? -1 : kb);      // slope index receiving a_dl
-  const int kr = above ? K : (below ? -1 : kb + 1);  // slope index receiving a_dr
-  // ---- knots -> bin sizes -> softmax logits ------------------------------------------------------
-  // knot j (1..K-1) = rmin + sum_{i<j} size_i ; knots 0 and K are constants (padding, rqSpline.py:329-333)
-  const bool lk = (!below && !above) && kb >= 1;      // left knot is a function of the parameters
-  const bool rk = (!below && !above) && kb + 1 <= K - 1;
-  float dotw = 0.0f, doth = 0.0f;
-  float apw[K], aph[K];
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    const float sel_l = (lk && i < kb) ? 1.0f : 0.0f;
-    const float sel_r = (rk && i < kb + 1) ? 1.0f : 0.0f;
-    apw[i] = scale * (sel_l * a_xl + sel_r * a_xr);
-    aph[i] = scale * (sel_l * a_yl + sel_r * a_yr);
-    dotw += pw[i] * apw[i];
-    doth += ph[i] * aph[i];
-  }
-#pragma unroll
-  for (int i = 0; i < K; ++i) {
-    draw[i] = pw[i] * (apw[i] - dotw);
-    draw[K + i] = ph[i] * (aph[i] - doth);
-  }
-#pragma unroll
-  for (int i = 0; i <= K; ++i) {
-    const float a_d = (i == kl ? a_dl : 0.0f) + (i == kr ? a_dr : 0.0f);
-    draw[2 * K + i] = (a_d != 0.0f) ? a_d * sigmoid_f(raw[2 * K + i] + offset) : 0.0f;
-  }
 }
 
 // dW[n][k] += sum_s A[s][n] * B[s][k]  and  db[n] += sum_s A[s][n]   (reduction over the tile's samples).
@@ -678,9 +554,13 @@ int64_t flowmc_flow_loss_grad_workspace_bytes(const FlowmcFlowDesc* D, int64_t n
   if (!D || n <= 0) return 0;
   const int64_t NP = 3 * D->num_bins + 1;
   // layer inputs + final latent, log-probs, and (tensor-core forward) the hidden activations and spline parameters
-  return 4 * (pad4i((int64_t)(D->n_layers + 1) * n * D->n_features) + pad4i(n) +
-              pad4i((int64_t)D->n_layers * (D->n_linear - 1) * 128 * n) +
-              pad4i((int64_t)D->n_layers * ((D->n_features + 1) / 2) * NP * n));
+  int64_t b = 4 * (pad4i((int64_t)(D->n_layers + 1) * n * D->n_features) + pad4i(n) +
+                   pad4i((int64_t)D->n_layers * (D->n_linear - 1) * 128 * n) +
+                   pad4i((int64_t)D->n_layers * ((D->n_features + 1) / 2) * NP * n));
+  if (flowmc::flow_backward_tc_supported(*D))  // transposed weight image + per-tile activation images
+    b += 1024 + ((flowmc::flow_backward_tc_wimg_bytes(*D) + 1023) & ~(int64_t)1023) +
+         flowmc::flow_backward_tc_act_bytes(*D, n);
+  return b;
 }
 
 int flowmc_flow_loss_grad(const FlowmcFlowDesc* D, const float* params, const float* x, const int32_t* idx,
@@ -705,7 +585,6 @@ int flowmc_flow_loss_grad(const FlowmcFlowDesc* D, const float* params, const fl
   float* logp = layer_inputs + pad4i((int64_t)(D->n_layers + 1) * n * D->n_features);
   float* save_h = logp + pad4i(n);
   float* save_theta = save_h + pad4i((int64_t)D->n_layers * (D->n_linear - 1) * 128 * n);
-  (void)NP;
   const bool tcf = flow_tc_enabled(*D);
   // The tensor-core forward can also hand its hidden activations and spline parameters to the backward kernel
   // (no conditioner recompute: -27 % instructions).  Measured on B200 (profiles/r01_flow_backward_c4_ncu.txt) the
@@ -716,6 +595,22 @@ int flowmc_flow_loss_grad(const FlowmcFlowDesc* D, const float* params, const fl
     const char* e = std::getenv("FLOWMC_BWD_SAVED");
     return e != nullptr && e[0] == '1';
   }();
+  static const bool bwd_tc = [] {
+    const char* e = std::getenv("FLOWMC_BWD_TC");
+    return e == nullptr || e[0] != '0';
+  }();
+  if (tcf && bwd_tc && flow_backward_tc_supported(*D)) {
+    // tensor-core forward AND backward: the forward leaves the spline parameters and the packed activation
+    // images behind, the backward (flow_train_tc.cu) runs every data / weight gradient GEMM on tcgen05
+    uint8_t* wimg = reinterpret_cast<uint8_t*>(save_theta + pad4i((int64_t)D->n_layers * ((D->n_features + 1) / 2) * NP * n));
+    wimg += (1024 - (reinterpret_cast<uintptr_t>(wimg) & 1023)) & 1023;
+    uint8_t* act_img = wimg + ((flow_backward_tc_wimg_bytes(*D) + 1023) & ~(int64_t)1023);
+    if (int rc = flow_transform_tc(*D, false, params, x, n, nullptr, logp, PRE_WHITEN, POST_BASE_LOGP, nullptr,
+                                   Key{0, 0}, 1, stream, idx, layer_inputs, nullptr, save_theta, act_img))
+      return rc;
+    return flow_backward_tc(*D, params, wimg, act_img, layer_inputs, save_theta, logp, n, inv_n_total, grad, loss,
+                            stream);
+  }
   if (tcf) {
     if (!use_saved) {
       save_h = nullptr;
