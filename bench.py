@@ -350,10 +350,13 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    try:
-        extras = flow_extras(dev)
-    except Exception as ex:  # the headline line must still be printed
-        extras = {"error": repr(ex)}
+    # FLOWMC_BENCH_EXTRAS=0 skips the flow add-ons (used for the ncu launch list of the timed step itself)
+    extras = {"skipped": "FLOWMC_BENCH_EXTRAS=0"}
+    if os.environ.get("FLOWMC_BENCH_EXTRAS", "1") != "0":
+        try:
+            extras = flow_extras(dev)
+        except Exception as ex:  # the headline line must still be printed
+            extras = {"error": repr(ex)}
     peak, peak_src = measured_peak()
     avg_kernel_ms = float(np.mean(kernel_ms))
     achieved = n * N_LOCAL_STEPS * BYTES_PER_CHAIN_STEP / (avg_kernel_ms * 1e-3) / 1e9
