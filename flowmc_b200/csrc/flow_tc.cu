@@ -26,6 +26,7 @@
 
 #include "flow_tc.cuh"
 #include "flow_tile.cuh"
+#include "flow_train.cuh"
 #include "registry.h"
 
 namespace flowmc {
@@ -642,7 +643,10 @@ extern "C" {
 
 // diagnostics: device buffer of 3 * 256 int64 that CTA 0 of the next tensor-core flow launches stamps with clock64()
 // (NULL switches it off).  Not thread-safe; used by scripts/tc_timeline.py only.
-void flowmc_debug_tc_timing(long long* buf) { flowmc::g_tc_timing = buf; }
+void flowmc_debug_tc_timing(long long* buf) {
+  flowmc::g_tc_timing = buf;
+  flowmc::flow_backward_tc_set_timing(buf ? buf + 3 * 256 : nullptr);  // 4th row: backward epilogue thread 0
+}
 
 int64_t flowmc_flow_tc_image_bytes(const FlowmcFlowDesc* D) {
   using namespace flowmc;

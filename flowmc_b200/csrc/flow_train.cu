@@ -558,8 +558,8 @@ int64_t flowmc_flow_loss_grad_workspace_bytes(const FlowmcFlowDesc* D, int64_t n
                    pad4i((int64_t)D->n_layers * (D->n_linear - 1) * 128 * n) +
                    pad4i((int64_t)D->n_layers * ((D->n_features + 1) / 2) * NP * n));
   if (flowmc::flow_backward_tc_supported(*D))  // transposed weight image + per-tile activation images
-    b += 1024 + ((flowmc::flow_backward_tc_wimg_bytes(*D) + 1023) & ~(int64_t)1023) +
-         flowmc::flow_backward_tc_act_bytes(*D, n);
+    b += 2048 + ((flowmc::flow_backward_tc_wimg_bytes(*D) + 1023) & ~(int64_t)1023) +
+         flowmc::flow_backward_tc_act_bytes(*D, n) + flowmc::flow_backward_tc_partial_bytes(*D, n);
   return b;
 }
 
@@ -608,8 +608,9 @@ int flowmc_flow_loss_grad(const FlowmcFlowDesc* D, const float* params, const fl
     if (int rc = flow_transform_tc(*D, false, params, x, n, nullptr, logp, PRE_WHITEN, POST_BASE_LOGP, nullptr,
                                    Key{0, 0}, 1, stream, idx, layer_inputs, nullptr, save_theta, act_img))
       return rc;
+    float* partial = reinterpret_cast<float*>(act_img + ((flow_backward_tc_act_bytes(*D, n) + 1023) & ~(int64_t)1023));
     return flow_backward_tc(*D, params, wimg, act_img, layer_inputs, save_theta, logp, n, inv_n_total, grad, loss,
-                            stream);
+                            partial, stream);
   }
   if (tcf) {
     if (!use_saved) {

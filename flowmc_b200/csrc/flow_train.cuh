@@ -13,9 +13,14 @@ __device__ __forceinline__ float sigmoid_f(float t) { return 1.0f / (1.0f + expf
 //   raw[3K+1]  conditioner output;  x  input;  Gy = dL/dy,  Gld = dL/dlogdet
 //   -> gx = dL/dx (direct path),  draw[3K+1] = dL/draw.
 // Same arithmetic as rq_params / rq_forward for everything that decides the bin.
-template <int K>
+// FAST = hardware ex2 / lg2 / rcp approximations (1-2 ulp, no slow-path branches) for the tensor-core kernel, whose
+// epilogue is latency-bound; the gradients stay within ~1e-6 relative of the accurate version.
+template <int K, bool FAST = false>
 __device__ __forceinline__ void rq_backward(const float* raw, float rmin, float rmax, float x, float Gy, float Gld,
                                             float& gx, float* draw) {
+  auto EXP = [](float v) { return FAST ? fast_exp(v) : expf(v); };
+  auto RCP = [](float v) { return FAST ? fast_rcp(v) : 1.0f / v; };
+  auto SOFTPLUS = [](float v) { return FAST ? fast_softplus(v) : softplus_f(v); };
   const float size = rmax - rmin;
   const float scale = size - (float)K * 1e-4f;
   const float offset = 0.5411666035652161f;
@@ -28,8 +33,8 @@ __device__ __forceinline__ void rq_backward(const float* raw, float rmin, float 
   float pw[K], ph[K], sw = 0.0f, sh = 0.0f;
 #pragma unroll
   for (int i = 0; i < K; ++i) {
-    pw[i] = expf(raw[i] - mw);
-    ph[i] = expf(raw[K + i] - mh);
+    pw[i] = EXP(raw[i] - mw);
+    ph[i] = EXP(raw[K + i] - mh);
     sw += pw[i];
     sh += ph[i];
   }
@@ -37,10 +42,11 @@ __device__ __forceinline__ void rq_backward(const float* raw, float rmin, float 
   xp[0] = rmin;
   yp[0] = rmin;
   float cx = 0.0f, cy = 0.0f;
+  const float rsw = RCP(sw), rsh = RCP(sh);
 #pragma unroll
   for (int i = 0; i < K; ++i) {
-    pw[i] = pw[i] / sw;
-    ph[i] = ph[i] / sh;
+    pw[i] = FAST ? pw[i] * rsw : pw[i] / sw;
+    ph[i] = FAST ? ph[i] * rsh : ph[i] / sh;
     if (i < K - 1) {
       const float bw = pw[i] * scale + 1e-4f;
       const float bh = ph[i] * scale + 1e-4f;
@@ -66,11 +72,12 @@ __device__ __forceinline__ void rq_backward(const float* raw, float rmin, float 
   const bool below = x <= xp[0], above = x >= xp[K];
   if (below) { ul = raw[2 * K]; }
   if (above) { ur = raw[3 * K]; }
-  const float dl = softplus_f(ul + offset) + 1e-4f, dr = softplus_f(ur + offset) + 1e-4f;
+  const float dl = SOFTPLUS(ul + offset) + 1e-4f, dr = SOFTPLUS(ur + offset) + 1e-4f;
 
   const float bw = xr - xl, bh = yr - yl;
-  const float s = bh / bw;
-  float z = (x - xl) / bw;
+  const float rbw = RCP(bw);
+  const float s = FAST ? bh * rbw : bh / bw;
+  float z = FAST ? (x - xl) * rbw : (x - xl) / bw;
   z = fminf(fmaxf(z, 0.0f), 1.0f);
   const float sq_z = z * z, z1mz = z - sq_z, omz = 1.0f - z, sq_1mz = omz * omz;
   const float st = dr + dl - 2.0f * s;
@@ -78,18 +85,21 @@ __device__ __forceinline__ void rq_backward(const float* raw, float rmin, float 
   const float den = s + st * z1mz;
   const float q = dr * sq_z + 2.0f * s * z1mz + dl * sq_1mz;
   // ---- reverse pass, in-range branch --------------------------------------------------------
-  const float a_num = Gy / den;
-  float a_den = -Gy * (bh * nu) / (den * den) - 2.0f * Gld / den;
-  const float a_q = Gld / q;
-  float a_s = 2.0f * Gld / s + a_q * 2.0f * z1mz + a_den * (1.0f - 2.0f * z1mz) + a_num * bh * sq_z;
+  const float rden = RCP(den);
+  const float a_num = FAST ? Gy * rden : Gy / den;
+  float a_den = FAST ? -Gy * (bh * nu) * (rden * rden) - 2.0f * Gld * rden
+                     : -Gy * (bh * nu) / (den * den) - 2.0f * Gld / den;
+  const float a_q = FAST ? Gld * RCP(q) : Gld / q;
+  float a_s = (FAST ? 2.0f * Gld * RCP(s) : 2.0f * Gld / s) + a_q * 2.0f * z1mz + a_den * (1.0f - 2.0f * z1mz) +
+              a_num * bh * sq_z;
   float a_dr = a_q * sq_z + a_den * z1mz;
   float a_dl = a_q * sq_1mz + a_den * z1mz + a_num * bh * z1mz;
   const float a_z = a_q * (2.0f * dr * z + 2.0f * s * (1.0f - 2.0f * z) - 2.0f * dl * omz) +
                     a_den * st * (1.0f - 2.0f * z) + a_num * bh * (2.0f * s * z + dl * (1.0f - 2.0f * z));
-  float a_bh = a_num * nu + a_s / bw;
-  float a_bw = -a_z * z / bw - a_s * s / bw;
-  gx = a_z / bw;
-  float a_xl = -a_z / bw - a_bw;
+  float a_bh = FAST ? a_num * nu + a_s * rbw : a_num * nu + a_s / bw;
+  float a_bw = FAST ? -(a_z * z + a_s * s) * rbw : -a_z * z / bw - a_s * s / bw;
+  gx = FAST ? a_z * rbw : a_z / bw;
+  float a_xl = -gx - a_bw;
   float a_xr = a_bw;
   float a_yl = Gy - a_bh;
   float a_yr = a_bh;
@@ -98,7 +108,7 @@ __device__ __forceinline__ void rq_backward(const float* raw, float rmin, float 
     const float de = below ? dl : dr;
     const float xe = below ? xp[0] : xp[K];
     gx = Gy * de;
-    const float a_de = Gy * (x - xe) + Gld / de;
+    const float a_de = Gy * (x - xe) + (FAST ? Gld * RCP(de) : Gld / de);
     a_dl = below ? a_de : 0.0f;
     a_dr = above ? a_de : 0.0f;
     a_xl = a_xr = a_yl = a_yr = 0.0f;
@@ -125,11 +135,11 @@ __device__ __forceinline__ void rq_backward(const float* raw, float rmin, float 
     draw[i] = pw[i] * (apw[i] - dotw);
     draw[K + i] = ph[i] * (aph[i] - doth);
   }
+  // softplus'(u) = sigmoid(u): only the (at most) two slopes of the selected bin receive gradient
+  const float gl = a_dl * (FAST ? fast_rcp(1.0f + fast_exp(-(ul + offset))) : sigmoid_f(ul + offset));
+  const float gr = a_dr * (FAST ? fast_rcp(1.0f + fast_exp(-(ur + offset))) : sigmoid_f(ur + offset));
 #pragma unroll
-  for (int i = 0; i <= K; ++i) {
-    const float a_d = (i == kl ? a_dl : 0.0f) + (i == kr ? a_dr : 0.0f);
-    draw[2 * K + i] = (a_d != 0.0f) ? a_d * sigmoid_f(raw[2 * K + i] + offset) : 0.0f;
-  }
+  for (int i = 0; i <= K; ++i) draw[2 * K + i] = (i == kl ? gl : 0.0f) + (i == kr ? gr : 0.0f);
 }
 
 
@@ -137,8 +147,10 @@ __device__ __forceinline__ void rq_backward(const float* raw, float rmin, float 
 bool flow_backward_tc_supported(const FlowmcFlowDesc& D);
 int64_t flow_backward_tc_wimg_bytes(const FlowmcFlowDesc& D);
 int64_t flow_backward_tc_act_bytes(const FlowmcFlowDesc& D, int64_t n);
+void flow_backward_tc_set_timing(long long* buf);
+int64_t flow_backward_tc_partial_bytes(const FlowmcFlowDesc& D, int64_t n);
 int flow_backward_tc(const FlowmcFlowDesc& D, const float* params, uint8_t* wimg, const uint8_t* act_img,
                      const float* save_x, const float* save_theta, const float* logp, int64_t n, float inv_n,
-                     float* grad, float* loss, cudaStream_t stream);
+                     float* grad, float* loss, float* partial, cudaStream_t stream);
 
 }  // namespace flowmc

@@ -33,6 +33,7 @@ namespace flowmc {
 constexpr int BT_STAGES = 3;
 constexpr int BT_TS = 132;  // row stride (floats) of the transpose buffer T[k][row]: conflict-free 128-bit reads
 constexpr int BT_MAX_ITEMS = 80;
+constexpr int BT_MAX_CTAS = 148;  // persistent CTAs, each with a private gradient accumulator
 
 enum : int { BK_DG3 = 0, BK_WG3 = 1, BK_DGH = 2, BK_WGH = 3 };
 
@@ -139,14 +140,24 @@ struct BtArgs {
   const float* logp;       // [n]
   int64_t n;
   float inv_n;
-  float* grad;
+  float* grad;         // final gradient (written by bt_reduce_kernel)
   float* loss;
+  float* partial;      // [gridDim.x][pstride]: this CTA's private gradient accumulator (no atomics, fixed order)
+  int64_t pstride;     // floats per CTA: L * layer_stride + 4 (the last 4: loss partial)
+  int64_t n_tiles;
+  long long* timing;  // optional diagnostics: clock64 stamps of epilogue thread 0 of CTA 0
 };
+
+#define BT_STAMP()                                                                                \
+  do {                                                                                            \
+    if (a.timing != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 256) a.timing[n_stamp++] = clock64(); \
+  } while (0)
 
 struct BtSmem {
   uint64_t stage_full[BT_STAGES], stage_empty[BT_STAGES], acc_full, a_ready;
   uint32_t tmem_base;
   float red[2 * TC_EPI_WARPS];
+  float bsum[TC_PARTS][TC_M];
 };
 
 template <int KB>
@@ -164,7 +175,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* P = a.params;
   const int L = D.n_layers, nh = D.n_linear - 1;
-  const int64_t row0 = (int64_t)blockIdx.x * TC_M;
   const int64_t n = a.n;
 
   if (warp == TC_EPI_WARPS + 1 && lane == 0) {
@@ -186,10 +196,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
   if (warp == TC_EPI_WARPS) {
     // ===== B-stage producer ====================================================================
     uint32_t s = 0, ph = 0;
+    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
     for (int l = L - 1; l >= 0; --l) {
       const int p = l & 1;
       const uint8_t* wbase = a.wimg + bt_layer_base(PR, l);
-      const uint8_t* abase = a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D);
+      const uint8_t* abase = a.act_img + (tile * L + l) * tc_act_layer_bytes(D);
       for (int ii = 0; ii < PR.n_items[p]; ++ii) {
         const BtItem it = PR.items[p][ii];
         const uint32_t bytes = 2u * it.N * 128u;
@@ -208,6 +219,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
   } else if (warp == TC_EPI_WARPS + 1) {
     // ===== MMA issuer ==========================================================================
     uint32_t s = 0, ph = 0, a_ph = 0;
+    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
     for (int l = L - 1; l >= 0; --l) {
       const int p = l & 1;
       for (int ii = 0; ii < PR.n_items[p]; ++ii) {
@@ -249,12 +261,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
     const int q = warp & 3, hf = warp >> 2;
     const int t = q * 32 + lane;                 // sample row (row work) or output unit (transposed work)
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const int64_t grow = row0 + t;
-    const bool valid = grow < n;
-    const int64_t r = valid ? grow : n - 1;
     float* gr = g + t * gs;
-    const float gld = valid ? -a.inv_n : 0.0f;  // dL/dlogdet of this row
     uint32_t f_ph = 0;
+    int n_stamp = 0;
     auto part = [&](int cnt, int& lo, int& hi) {
       const int per = (cnt + TC_PARTS - 1) / TC_PARTS;
       lo = min(cnt, hf * per);
@@ -262,19 +271,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
     };
     int j_lo, j_hi;
     part(d, j_lo, j_hi);
-
-    // loss contribution and dL/dy of the final latent: loss = -mean(logdet + base.log_prob(y))
-    if (hf == 0) {
-      float v = valid ? a.logp[grow] : 0.0f;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) atomicAdd(a.loss, -v * a.inv_n);
-    }
-    for (int j = j_lo; j < j_hi; ++j) {
-      const float y = a.save_x[((int64_t)L * n + r) * d + j];
-      gr[j] = valid ? a.inv_n * (y - P[D.off_base_mean + j]) / P[D.off_base_cov + (int64_t)j * d + j] : 0.0f;
-    }
-    epi_bar();
+    float* PB = a.partial + (int64_t)blockIdx.x * a.pstride;  // private accumulator of this CTA
 
     // hands the A operand to the MMA warp and waits for the item's accumulator
     auto run_item = [&]() {
@@ -306,14 +303,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
       return bsum;
     };
 
+    // acc 1 (lane = output unit m, columns [0, ncols)) -> T[m][c] row-major, so that the rows can then be written to
+    // global memory with full 512-byte coalescing (a thread owning a whole row would touch 32 sectors per store)
+    auto stage_acc1 = [&](int ncols) {
+      for (int c = hf * 64; c < min(ncols, hf * 64 + 64); c += 16) {
+        float v[16];
+        tc::tmem_ld16(tbase + 384 + lane_base + c, v);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 16; u += 4)
+          *reinterpret_cast<float4*>(T + t * BT_TS + c + u) = make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]);
+      }
+    };
+    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const bool first = tile == (int64_t)blockIdx.x;  // first tile of this CTA: store, later tiles: accumulate
+    auto acc_to = [&](float* ptr, float v) { *ptr = first ? v : *ptr + v; };
+    // one warp per row of the staged dW tile: lanes cover 4 consecutive columns each
+    auto write_row = [&](int m, float* dst, int ncols) {
+      const int c = lane * 4;
+      if (c < ncols) {
+        float4 v = *reinterpret_cast<const float4*>(T + m * BT_TS + c);
+        float4* gp = reinterpret_cast<float4*>(dst + c);
+        if (!first) {
+          const float4 o = *gp;
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        *gp = v;
+      }
+    };
+    const int64_t row0 = tile * TC_M;
+    const int64_t grow = row0 + t;
+    const bool valid = grow < n;
+    const int64_t r = valid ? grow : n - 1;
+    const float gld = valid ? -a.inv_n : 0.0f;  // dL/dlogdet of this row
+    // loss contribution and dL/dy of the final latent: loss = -mean(logdet + base.log_prob(y))
+    if (hf == 0) {
+      float v = valid ? a.logp[grow] : 0.0f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) S->red[warp] = -v * a.inv_n;
+    }
+    for (int j = j_lo; j < j_hi; ++j) {
+      const float y = a.save_x[((int64_t)L * n + r) * d + j];
+      gr[j] = valid ? a.inv_n * (y - P[D.off_base_mean + j]) / P[D.off_base_cov + (int64_t)j * d + j] : 0.0f;
+    }
+    epi_bar();
+    if (tid == 0) acc_to(PB + a.pstride - 4, (S->red[0] + S->red[1]) + (S->red[2] + S->red[3]));
     for (int l = L - 1; l >= 0; --l) {
       const int p = l & 1;
       const float* PL = P + (int64_t)l * D.layer_stride;
-      float* GL = a.grad + (int64_t)l * D.layer_stride;
+      float* GL = PB + (int64_t)l * D.layer_stride;
       const float scale = PL[D.off_scale], shift = PL[D.off_shift];
       const float e = expf(scale);
       const float* xin = a.save_x + ((int64_t)l * n + r) * d;  // this row's layer input (before the ScalarAffine)
-      const uint8_t* abase = a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D);
+      const uint8_t* abase = a.act_img + (tile * L + l) * tc_act_layer_bytes(D);
       const int H = D.dims[nh];
       int ii = 0;
       // ---- spline chunks -----------------------------------------------------------------------
@@ -328,7 +371,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
 #pragma unroll
           for (int u = 0; u < NP; ++u) raw[u] = th[(int64_t)u * n];
           const float xa = (xin[f] + shift) * e;
-          rq_backward<KB>(raw, D.range_min, D.range_max, xa, gr[f], gld, gx, dr);
+          rq_backward<KB, true>(raw, D.range_min, D.range_max, xa, gr[f], gld, gx, dr);
           gr[f] = gx;
           // dtheta -> A (lane = this row, columns fi*32 .. fi*32+31) and the transpose buffer T[column][row]
           if (NP <= 32) {
@@ -348,30 +391,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
             }
           }
         }
+        BT_STAMP();  // spline adjoints + operand written
         run_item();  // dh_last (+)= dtheta W3_c   (acc 0)
+        BT_STAMP();  // data-gradient MMAs done
         epi_bar();   // T complete
-        {
-          const float bsum = write_transposed();
-          const int fi = t >> 5, rr = t & 31;
-          if (fi < it.n_feat && rr < NP) atomicAdd(GL + D.off_b[nh] + (p + 2 * (it.lin + fi)) * NP + rr, bsum);
-        }
+        S->bsum[hf][t] = write_transposed();
+        BT_STAMP();  // transposed operand written
         run_item();  // dW3_c = dtheta^T h_last   (acc 1)
-        {
-          const int fi = t >> 5, rr = t & 31;
-          const bool ok = fi < it.n_feat && rr < NP;
-          float* dst = GL + D.off_W[nh] + ((int64_t)(p + 2 * (it.lin + fi)) * NP + rr) * H;
-          for (int c = hf * 64; c < min(H, hf * 64 + 64); c += 16) {
-            float v[16];
-            tc::tmem_ld16(tbase + 384 + lane_base + c, v);
-            tc::tmem_wait_ld();
-            if (ok) {
-#pragma unroll
-              for (int u = 0; u < 16; ++u)
-                if (c + u < H) atomicAdd(dst + c + u, v[u]);
-            }
+        BT_STAMP();  // weight-gradient MMAs done
+        stage_acc1(H);
+        epi_bar();
+        for (int m = warp; m < it.n_feat * 32; m += TC_EPI_WARPS) {
+          const int fi = m >> 5, rr = m & 31;
+          if (rr < NP) {
+            const int64_t prow = (int64_t)(p + 2 * (it.lin + fi)) * NP + rr;
+            write_row(m, GL + D.off_W[nh] + prow * H, H);
+            if (lane == 0)  // bias gradient = row sum of dtheta^T (both halves of the tile's samples)
+              acc_to(GL + D.off_b[nh] + prow, S->bsum[0][m] + S->bsum[1][m]);
           }
         }
-        epi_bar();  // T and acc 1 free for the next chunk
+        epi_bar();  // T, bsum and acc 1 free for the next chunk
+        BT_STAMP();  // dW tile reduced into the gradient
       }
       // ---- tanh layers in reverse ----------------------------------------------------------------
       for (; ii < PR.n_items[p]; ii += 2) {
@@ -404,24 +444,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
         }
         run_item();  // dh_prev = da W_i  (acc 0; for i == 0: the conditioner-input gradient)
         epi_bar();
-        {
-          const float bsum = write_transposed();
-          if (t < N) atomicAdd(GL + D.off_b[i] + t, bsum);
-        }
+        S->bsum[hf][t] = write_transposed();
         run_item();  // dW_i = da^T in_i   (acc 1)
         {
           const int Kin = D.dims[i];
-          float* dst = GL + D.off_W[i] + (int64_t)t * Kin;
-          const int c_end = min(tc_pad16(Kin), hf * 64 + 64);
-          for (int c = hf * 64; c < c_end; c += 16) {
-            float v[16];
-            tc::tmem_ld16(tbase + 384 + lane_base + c, v);
-            tc::tmem_wait_ld();
-            if (t < N) {
-#pragma unroll
-              for (int u = 0; u < 16; ++u)
-                if (c + u < Kin && (i > 0 || ((c + u + l) & 1) == 1)) atomicAdd(dst + c + u, v[u]);
+          stage_acc1(tc_pad16(Kin));
+          epi_bar();
+          for (int m = warp; m < N; m += TC_EPI_WARPS) {
+            float* dst = GL + D.off_W[i] + (int64_t)m * Kin;
+            if (i > 0) {
+              write_row(m, dst, Kin);  // hidden widths are multiples of 16: whole float4 columns
+            } else {
+              // first Linear: only the conditioning inputs ((j + l) odd) carry gradient; d need not be a multiple of 4
+              for (int c = lane; c < Kin; c += 32)
+                if (((c + l) & 1) == 1) acc_to(dst + c, T[m * BT_TS + c]);
             }
+            if (lane == 0) acc_to(GL + D.off_b[i] + m, S->bsum[0][m] + S->bsum[1][m]);
           }
         }
         epi_bar();
@@ -465,17 +503,57 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
             sb += S->red[TC_EPI_WARPS + w];
           }
           const int n_valid = (int)min((int64_t)TC_M, n - row0);
-          atomicAdd(GL + D.off_scale, sa - a.inv_n * (float)d * (float)n_valid);
-          atomicAdd(GL + D.off_shift, sb);
+          acc_to(GL + D.off_scale, sa - a.inv_n * (float)d * (float)n_valid);
+          acc_to(GL + D.off_shift, sb);
         }
         epi_bar();
       }
     }
+    }  // tiles
     tc::tc_fence_before();
   }
   __syncthreads();
   tc::tc_fence_after();
   if (warp == TC_EPI_WARPS) tc::tmem_dealloc<512>(tbase);
+}
+
+// grad[i] = sum over CTAs of their private accumulators, in CTA order (deterministic).  Entries no CTA writes
+// (alignment padding, W3 / b3 rows of the features a layer does not transform, W1 columns of the masked inputs) are
+// recognised from the index and left at zero.
+__global__ void bt_reduce_kernel(const FlowmcFlowDesc D, const float* __restrict__ partial, int64_t pstride, int n_cta,
+                                 float* __restrict__ grad, float* __restrict__ loss) {
+  const int nh = D.n_linear - 1, NP = 3 * D.num_bins + 1, d = D.n_features;
+  const int64_t total = (int64_t)D.n_layers * D.layer_stride;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int l = (int)(i / D.layer_stride);
+    const int64_t o = i - (int64_t)l * D.layer_stride;
+    bool live = false;
+    if (o >= D.off_W[nh] && o < D.off_W[nh] + (int64_t)D.dims[nh + 1] * D.dims[nh]) {
+      const int f = (int)((o - D.off_W[nh]) / D.dims[nh]) / NP;
+      live = ((f ^ l) & 1) == 0;
+    } else if (o >= D.off_b[nh] && o < D.off_b[nh] + D.dims[nh + 1]) {
+      live = ((((int)(o - D.off_b[nh]) / NP) ^ l) & 1) == 0;
+    } else if (o >= D.off_W[0] && o < D.off_W[0] + (int64_t)D.dims[1] * d) {
+      live = ((((int)((o - D.off_W[0]) % d)) + l) & 1) == 1;
+    } else if (o == D.off_scale || o == D.off_shift) {
+      live = true;
+    } else {
+      for (int k = 0; k < nh; ++k) {
+        if (k > 0 && o >= D.off_W[k] && o < D.off_W[k] + (int64_t)D.dims[k + 1] * D.dims[k]) live = true;
+        if (o >= D.off_b[k] && o < D.off_b[k] + D.dims[k + 1]) live = true;
+      }
+    }
+    if (live) {
+      float s = 0.0f;
+      for (int c = 0; c < n_cta; ++c) s += partial[(int64_t)c * pstride + i];
+      grad[i] = s;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.0f;
+    for (int c = 0; c < n_cta; ++c) s += partial[(int64_t)c * pstride + pstride - 4];
+    *loss = s;
+  }
 }
 
 template <int KB>
@@ -491,7 +569,10 @@ static int launch_bt(const FlowmcFlowDesc& D, const BtProgram& PR, const BtArgs&
     }
     configured = bytes;
   }
-  kern<<<(unsigned)((a.n + TC_M - 1) / TC_M), TC_THREADS, bytes, stream>>>(D, PR, a);
+  const int n_cta = (int)(a.n_tiles < BT_MAX_CTAS ? a.n_tiles : BT_MAX_CTAS);
+  kern<<<n_cta, TC_THREADS, bytes, stream>>>(D, PR, a);
+  flowmc_count_launch();
+  bt_reduce_kernel<<<148 * 4, 256, 0, stream>>>(D, a.partial, a.pstride, n_cta, a.grad, a.loss);
   flowmc_count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -500,6 +581,9 @@ static int launch_bt(const FlowmcFlowDesc& D, const BtProgram& PR, const BtArgs&
   }
   return FLOWMC_OK;
 }
+
+static long long* g_bt_timing = nullptr;
+void flow_backward_tc_set_timing(long long* buf) { g_bt_timing = buf; }
 
 bool flow_backward_tc_supported(const FlowmcFlowDesc& D) {
   if (!tc_supported(D)) return false;
@@ -521,9 +605,14 @@ int64_t flow_backward_tc_act_bytes(const FlowmcFlowDesc& D, int64_t n) {
   return ((n + TC_M - 1) / TC_M) * (int64_t)D.n_layers * (int64_t)tc_act_layer_bytes(D);
 }
 
+int64_t flow_backward_tc_partial_bytes(const FlowmcFlowDesc& D, int64_t n) {
+  const int64_t tiles = (n + TC_M - 1) / TC_M;
+  return (tiles < BT_MAX_CTAS ? tiles : BT_MAX_CTAS) * ((int64_t)D.n_layers * D.layer_stride + 4) * 4;
+}
+
 int flow_backward_tc(const FlowmcFlowDesc& D, const float* params, uint8_t* wimg, const uint8_t* act_img,
                      const float* save_x, const float* save_theta, const float* logp, int64_t n, float inv_n,
-                     float* grad, float* loss, cudaStream_t stream) {
+                     float* grad, float* loss, float* partial, cudaStream_t stream) {
   BtProgram PR;
   if (int rc = bt_build_program(D, &PR)) return rc;
   const int items = PR.n_items[0] > PR.n_items[1] ? PR.n_items[0] : PR.n_items[1];
@@ -531,7 +620,8 @@ int flow_backward_tc(const FlowmcFlowDesc& D, const float* params, uint8_t* wimg
   flowmc_count_launch();
   BtArgs a;
   a.params = params; a.wimg = wimg; a.act_img = act_img; a.save_x = save_x; a.save_theta = save_theta; a.logp = logp;
-  a.n = n; a.inv_n = inv_n; a.grad = grad; a.loss = loss;
+  a.n = n; a.inv_n = inv_n; a.grad = grad; a.loss = loss; a.timing = g_bt_timing;
+  a.partial = partial; a.pstride = (int64_t)D.n_layers * D.layer_stride + 4; a.n_tiles = (n + TC_M - 1) / TC_M;
   switch (D.num_bins) {
     case 4: return launch_bt<4>(D, PR, a, stream);
     case 8: return launch_bt<8>(D, PR, a, stream);

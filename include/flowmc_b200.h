@@ -239,7 +239,8 @@ FLOWMC_API int flowmc_debug_tc_gemm(const float* A, const float* W, int N, int K
                                     float* scratch, void* stream);
 
 /* diagnostics: CTA 0 of subsequent tensor-core flow launches stamps clock64() at its pipeline events into buf
- * (device, 3 * 256 int64: weight producer / MMA issuer / epilogue thread 0); NULL switches it off */
+ * (device, 4 * 256 int64: weight producer / MMA issuer / epilogue thread 0 of the forward kernel, epilogue thread 0
+ * of the tensor-core backward kernel); NULL switches it off */
 FLOWMC_API void flowmc_debug_tc_timing(long long* buf);
 
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */

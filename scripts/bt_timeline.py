@@ -1,0 +1,25 @@
+"""Timeline (clock64) of epilogue thread 0, CTA 0 of the tensor-core backward kernel for one C4 training step."""
+import sys
+sys.path.insert(0, "/root/repo")
+import torch
+from flowmc_b200 import random as frandom
+from flowmc_b200._lib import lib
+from flowmc_b200.resource.model.nf_model.rqSpline import MaskedCouplingRQSpline
+
+d, L = (32, 10) if (len(sys.argv) < 2 or sys.argv[1] == "c4") else (64, 8)
+m = MaskedCouplingRQSpline(d, L, [128, 128], 8, frandom.PRNGKey(1))
+x = frandom.normal(frandom.PRNGKey(2), (16384, d))
+m.loss_and_grad(x)
+buf = torch.zeros(4 * 256, dtype=torch.int64, device="cuda")
+lib.flowmc_debug_tc_timing(buf.data_ptr())
+m.loss_and_grad(x)
+torch.cuda.synchronize()
+lib.flowmc_debug_tc_timing(None)
+t = buf.cpu().numpy().reshape(4, 256)[3]
+v = t[t > 0]
+v = v - v[0]
+print("backward epilogue stamps per chunk: [operand written, dgrad done, transposed written, wgrad done, reduced]")
+print(" ".join(str(int(c)) for c in v[:60]))
+import numpy as np
+dv = np.diff(v[:41])
+print("deltas:", " ".join(str(int(c)) for c in dv))
