@@ -34,7 +34,7 @@ namespace flowmc {
 constexpr int TC_STAGES = 4;
 constexpr int TC_MAX_ITEMS = 40;
 
-enum : int { TC_FWD = 0, TC_INV = 1, TC_NF = 2 };
+enum : int { TC_FWD = 0, TC_INV = 1, TC_NF = 2, TC_TRAIN = 3 };  // TRAIN = FWD + activation dump for the backward
 
 struct TcItem {
   int kind;      // 0: hidden Linear (+tanh), 1: chunk of spline features
@@ -352,15 +352,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
         xr[j] = v;
       }
     }
-    for (int l = 0; l < L; ++l) {  // stage the biases (visible after the first epi_bar below)
-      const float* PL = P + (int64_t)l * D.layer_stride;
-      float* sb = sbias_all + l * bias_stride;
-      const int p = l & 1, ntf = (d - p + 1) / 2;
-      for (int i = 0; i < nh; ++i)
-        for (int c = tid; c < D.dims[i + 1]; c += TC_EPI) sb[i * 128 + c] = PL[D.off_b[i] + c];
-      for (int c = tid; c < ntf * NP; c += TC_EPI) {
-        const int o = c / NP, rr = c - o * NP;
-        sb[nh * 128 + c] = PL[D.off_b[nh] + (p + 2 * o) * NP + rr];
+    // stage every layer's biases (visible after the first epi_bar below).  Flattened over (layer, entry) with 8
+    // independent loads in flight per thread: the naive per-layer loop cost ~16K cycles of serialised L2 latency.
+    {
+      const int total = L * bias_stride;
+      for (int base = 0; base < total; base += 8 * TC_EPI) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = base + u * TC_EPI + tid;
+          v[u] = 0.0f;
+          if (e < total) {
+            const int l = e / bias_stride, c = e - l * bias_stride;
+            const float* PL = P + (int64_t)l * D.layer_stride;
+            if (c < nh * 128) {
+              const int i = c >> 7, cc = c & 127;
+              if (cc < D.dims[i + 1]) v[u] = PL[D.off_b[i] + cc];
+            } else {
+              const int c2 = c - nh * 128, o = c2 / NP, rr = c2 - o * NP, p = l & 1;
+              if (o < (d - p + 1) / 2) v[u] = PL[D.off_b[nh] + (p + 2 * o) * NP + rr];
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = base + u * TC_EPI + tid;
+          if (e < total) sbias_all[e] = v[u];
+        }
       }
     }
     float ldacc = 0.0f;
@@ -375,7 +393,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
         const float* PL = P + (int64_t)l * D.layer_stride;
         const float scale = PL[D.off_scale], shift = PL[D.off_shift];
         const float* sbias = sbias_all + l * bias_stride;
-        if (MODE == TC_FWD && a.save_x != nullptr && grow < a.n)
+        if (MODE == TC_TRAIN && a.save_x != nullptr && grow < a.n)
           for (int j = j_lo; j < j_hi; ++j) a.save_x[((int64_t)l * a.n + grow) * d + j] = xr[j];
         // ---- ScalarAffine (rqSpline.py:435-436) + A operand = x * mask, hi / lo ------------------
         {
@@ -396,7 +414,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
             }
             tc::tmem_st8(t_ahi + lane_base + g * 8, hi);
             tc::tmem_st8(t_alo + lane_base + g * 8, lo);
-            if (MODE == TC_FWD && a.act_img != nullptr) {
+            if (MODE == TC_TRAIN && a.act_img != nullptr) {
               const int npx = tc_pad16(d);
               uint32_t* img = reinterpret_cast<uint32_t*>(a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) +
                                                           (size_t)q * 2 * npx * 128);
@@ -439,10 +457,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
               for (int u = 0; u < 16; ++u) {
                 const float hv = tanh_ex2(v[u] + bias[c + u]);
                 tc::split_tf32(hv, hi[u], lo[u]);
-                if (MODE == TC_FWD && a.save_h != nullptr && grow < a.n)
+                if (MODE == TC_TRAIN && a.save_h != nullptr && grow < a.n)
                   a.save_h[((int64_t)(l * nh + it.lin) * 128 + c + u) * a.n + grow] = hv;
               }
-              if (MODE == TC_FWD && a.act_img != nullptr) {
+              if (MODE == TC_TRAIN && a.act_img != nullptr) {
                 uint32_t* img = reinterpret_cast<uint32_t*>(a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) +
                                                             tc_act_item_off(D, it.lin + 1) + (size_t)q * 2 * N * 128);
 #pragma unroll
@@ -481,7 +499,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
               }
 #pragma unroll
               for (int u = 0; u < NP && u < 32; ++u) raw[u] = v[u] + bl[i * NP + u];
-              if (MODE == TC_FWD && a.save_theta != nullptr && grow < a.n) {
+              if (MODE == TC_TRAIN && a.save_theta != nullptr && grow < a.n) {
                 float* dst = a.save_theta + ((int64_t)l * ((d + 1) / 2) + it.lin + i) * NP * a.n + grow;
 #pragma unroll
                 for (int u = 0; u < NP; ++u) dst[(int64_t)u * a.n] = raw[u];
@@ -533,7 +551,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     }
 
     // ---- epilogue of the tile ------------------------------------------------------------------
-    if (MODE == TC_FWD && a.save_x != nullptr && grow < a.n)
+    if (MODE == TC_TRAIN && a.save_x != nullptr && grow < a.n)
       for (int j = j_lo; j < j_hi; ++j) a.save_x[((int64_t)L * a.n + grow) * d + j] = xr[j];
     S->ldpart[hf][row] = ldacc;
     epi_bar();
@@ -620,7 +638,10 @@ int flow_transform_tc(const FlowmcFlowDesc& D, bool inverse, const float* P, con
   a.rows_per_key = rpk;
   a.save_x = save_x; a.save_h = save_h; a.save_theta = save_theta; a.act_img = act_img;
   a.timing = g_tc_timing;
-  return inverse ? dispatch_tc<TC_INV>(D, PR, a, stream) : dispatch_tc<TC_FWD>(D, PR, a, stream);
+  if (inverse) return dispatch_tc<TC_INV>(D, PR, a, stream);
+  if (save_x != nullptr || save_h != nullptr || save_theta != nullptr || act_img != nullptr)
+    return dispatch_tc<TC_TRAIN>(D, PR, a, stream);
+  return dispatch_tc<TC_FWD>(D, PR, a, stream);
 }
 
 int flow_nf_propose_tc(const FlowmcFlowDesc& D, const float* P, Key subkey, const uint32_t* chain_keys,
