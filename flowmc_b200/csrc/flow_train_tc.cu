@@ -273,63 +273,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
     part(d, j_lo, j_hi);
     float* PB = a.partial + (int64_t)blockIdx.x * a.pstride;  // private accumulator of this CTA
 
-    // hands the A operand to the MMA warp and waits for the item's accumulator
-    auto run_item = [&]() {
+    // ---- software pipeline -------------------------------------------------------------------------
+    // A "unit" is one (data-gradient, weight-gradient) pair of GEMMs: a chunk of spline features, or one tanh
+    // layer.  For unit u the epilogue threads
+    //   [A] write the prepared dY rows as the A operand                      -> dgrad MMAs of u start
+    //   [B] read dY back TRANSPOSED from shared memory into registers   }
+    //   [C] store the dW tile of unit u-1 (acc 1) into the accumulator  }    overlap the dgrad MMAs
+    //   [D] wait for the dgrad MMAs
+    //   [E] write dY^T as the A operand                                      -> wgrad MMAs of u start
+    //   [F] prepare unit u+1 (spline adjoints / tanh derivative; at a layer boundary first the masked-coupling
+    //       and ScalarAffine adjoints)                                       overlaps the wgrad MMAs
+    //   [G] wait for the wgrad MMAs.
+    // The A region of tensor memory is the only resource epilogue and MMA hand back and forth.
+    auto arrive_item = [&]() {
       tc::tmem_wait_st();
       tc::tc_fence_before();
       tc::mbar_arrive(&S->a_ready);
+    };
+    auto wait_item = [&]() {
       tc::mbar_wait(&S->acc_full, f_ph);
       f_ph ^= 1;
       tc::tc_fence_after();
     };
-    // A^T: output unit m = t reads its row of the transpose buffer (this thread: half of the tile's samples),
-    // writes it as TMEM lane m, and returns the row sum (= the bias gradient of unit m)
-    auto write_transposed = [&]() -> float {
-      float bsum = 0.0f;
-      const float* src = T + t * BT_TS;
-      for (int c = hf * 64; c < hf * 64 + 64; c += 8) {
-        const float4 v0 = *reinterpret_cast<const float4*>(src + c);
-        const float4 v1 = *reinterpret_cast<const float4*>(src + c + 4);
-        const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        uint32_t hi[8], lo[8];
+    // dY of this thread's row: two segments of up to 32 A columns each.  prepare() leaves the values in the
+    // transpose buffer (T[column][row], written by this same thread), write_arow() moves them into the A region.
+    int seg_base[2], seg_len[2];
+    auto write_arow = [&]() {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          bsum += v[u];
-          tc::split_tf32(v[u], hi[u], lo[u]);
+      for (int sg = 0; sg < 2; ++sg) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          if (c < seg_len[sg]) {
+            uint32_t hi[8], lo[8];
+            const float* src = T + (seg_base[sg] + c) * BT_TS + t;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) tc::split_tf32(src[u * BT_TS], hi[u], lo[u]);
+            tc::tmem_st8(t_ahi + lane_base + seg_base[sg] + c, hi);
+            tc::tmem_st8(t_alo + lane_base + seg_base[sg] + c, lo);
+          }
         }
-        tc::tmem_st8(t_ahi + lane_base + c, hi);
-        tc::tmem_st8(t_alo + lane_base + c, lo);
-      }
-      return bsum;
-    };
-
-    // acc 1 (lane = output unit m, columns [0, ncols)) -> T[m][c] row-major, so that the rows can then be written to
-    // global memory with full 512-byte coalescing (a thread owning a whole row would touch 32 sectors per store)
-    auto stage_acc1 = [&](int ncols) {
-      for (int c = hf * 64; c < min(ncols, hf * 64 + 64); c += 16) {
-        float v[16];
-        tc::tmem_ld16(tbase + 384 + lane_base + c, v);
-        tc::tmem_wait_ld();
-#pragma unroll
-        for (int u = 0; u < 16; u += 4)
-          *reinterpret_cast<float4*>(T + t * BT_TS + c + u) = make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]);
       }
     };
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const bool first = tile == (int64_t)blockIdx.x;  // first tile of this CTA: store, later tiles: accumulate
     auto acc_to = [&](float* ptr, float v) { *ptr = first ? v : *ptr + v; };
-    // one warp per row of the staged dW tile: lanes cover 4 consecutive columns each
-    auto write_row = [&](int m, float* dst, int ncols) {
-      const int c = lane * 4;
-      if (c < ncols) {
-        float4 v = *reinterpret_cast<const float4*>(T + m * BT_TS + c);
-        float4* gp = reinterpret_cast<float4*>(dst + c);
-        if (!first) {
-          const float4 o = *gp;
-          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-        }
-        *gp = v;
+    auto store4 = [&](float* ptr, const float* v) {
+      float4 w = make_float4(v[0], v[1], v[2], v[3]);
+      float4* gp = reinterpret_cast<float4*>(ptr);
+      if (!first) {
+        const float4 o = *gp;
+        w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w;
       }
+      *gp = w;
     };
     const int64_t row0 = tile * TC_M;
     const int64_t grow = row0 + t;
@@ -349,164 +344,222 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
     }
     epi_bar();
     if (tid == 0) acc_to(PB + a.pstride - 4, (S->red[0] + S->red[1]) + (S->red[2] + S->red[3]));
-    for (int l = L - 1; l >= 0; --l) {
+
+    // dY of the unit (layer l, items ii / ii + 1) -> the transpose buffer T[column][row] + this row's A segments
+    auto prepare = [&](int l, int ii) {
       const int p = l & 1;
+      const BtItem it = PR.items[p][ii];
       const float* PL = P + (int64_t)l * D.layer_stride;
-      float* GL = PB + (int64_t)l * D.layer_stride;
-      const float scale = PL[D.off_scale], shift = PL[D.off_shift];
-      const float e = expf(scale);
-      const float* xin = a.save_x + ((int64_t)l * n + r) * d;  // this row's layer input (before the ScalarAffine)
-      const uint8_t* abase = a.act_img + (tile * L + l) * tc_act_layer_bytes(D);
-      const int H = D.dims[nh];
-      int ii = 0;
-      // ---- spline chunks -----------------------------------------------------------------------
-      for (; ii < PR.n_items[p] && PR.items[p][ii].kind == BK_DG3; ii += 2) {
-        const BtItem it = PR.items[p][ii];
+      seg_len[0] = seg_len[1] = 0;
+      seg_base[0] = seg_base[1] = 0;
+      if (it.kind == BK_DG3) {
+        const float shift = PL[D.off_shift], e = expf(PL[D.off_scale]);
+        const float* xin = a.save_x + ((int64_t)l * n + r) * d;
         int i_lo, i_hi;
         part(it.n_feat, i_lo, i_hi);
-        for (int fi = i_lo; fi < i_hi; ++fi) {
-          const int fo = it.lin + fi, f = p + 2 * fo;
-          float raw[NP], dr[NP + 7], gx;
-          const float* th = a.save_theta + ((int64_t)l * ((d + 1) / 2) + fo) * NP * n + r;
 #pragma unroll
-          for (int u = 0; u < NP; ++u) raw[u] = th[(int64_t)u * n];
-          const float xa = (xin[f] + shift) * e;
-          rq_backward<KB, true>(raw, D.range_min, D.range_max, xa, gr[f], gld, gx, dr);
-          gr[f] = gx;
-          // dtheta -> A (lane = this row, columns fi*32 .. fi*32+31) and the transpose buffer T[column][row]
-          if (NP <= 32) {
+        for (int sg = 0; sg < 2; ++sg) {
+          const int fi = i_lo + sg;
+          if (fi < i_hi) {
+            const int fo = it.lin + fi, f = p + 2 * fo;
+            float raw[NP], dr[NP], gx;
+            const float* th = a.save_theta + ((int64_t)l * ((d + 1) / 2) + fo) * NP * n + r;
 #pragma unroll
-            for (int u = NP; u < NP + 7; ++u) dr[u] = 0.0f;
+            for (int u = 0; u < NP; ++u) raw[u] = th[(int64_t)u * n];
+            const float xa = (xin[f] + shift) * e;
+            rq_backward<KB, true>(raw, D.range_min, D.range_max, xa, gr[f], gld, gx, dr);
+            gr[f] = gx;
+            seg_base[sg] = fi * 32;
+            seg_len[sg] = 32;
 #pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-              uint32_t hi[8], lo[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const float v = (c + u < NP) ? dr[(c + u < NP) ? c + u : 0] : 0.0f;
-                tc::split_tf32(v, hi[u], lo[u]);
-                T[(fi * 32 + c + u) * BT_TS + t] = v;
-              }
-              tc::tmem_st8(t_ahi + lane_base + fi * 32 + c, hi);
-              tc::tmem_st8(t_alo + lane_base + fi * 32 + c, lo);
+            for (int u = 0; u < 32; ++u) {
+              T[(fi * 32 + u) * BT_TS + t] = (u < NP) ? dr[u < NP ? u : 0] : 0.0f;
             }
           }
         }
-        BT_STAMP();  // spline adjoints + operand written
-        run_item();  // dh_last (+)= dtheta W3_c   (acc 0)
-        BT_STAMP();  // data-gradient MMAs done
-        epi_bar();   // T complete
-        S->bsum[hf][t] = write_transposed();
-        BT_STAMP();  // transposed operand written
-        run_item();  // dW3_c = dtheta^T h_last   (acc 1)
-        BT_STAMP();  // weight-gradient MMAs done
-        stage_acc1(H);
-        epi_bar();
-        for (int m = warp; m < it.n_feat * 32; m += TC_EPI_WARPS) {
-          const int fi = m >> 5, rr = m & 31;
-          if (rr < NP) {
-            const int64_t prow = (int64_t)(p + 2 * (it.lin + fi)) * NP + rr;
-            write_row(m, GL + D.off_W[nh] + prow * H, H);
-            if (lane == 0)  // bias gradient = row sum of dtheta^T (both halves of the tile's samples)
-              acc_to(GL + D.off_b[nh] + prow, S->bsum[0][m] + S->bsum[1][m]);
-          }
-        }
-        epi_bar();  // T, bsum and acc 1 free for the next chunk
-        BT_STAMP();  // dW tile reduced into the gradient
-      }
-      // ---- tanh layers in reverse ----------------------------------------------------------------
-      for (; ii < PR.n_items[p]; ii += 2) {
-        const BtItem it = PR.items[p][ii];
-        const int i = it.lin;
-        const int N = D.dims[i + 1];  // width of this hidden layer
+      } else {
         // da = dh (1 - h^2): dh from acc 0, h from the forward pass's activation image (hi + lo)
-        {
-          const uint32_t* himg = reinterpret_cast<const uint32_t*>(abase + tc_act_item_off(D, i + 1) + (size_t)q * 2 * N * 128);
-          int c_lo, c_hi;
-          part(N / 16, c_lo, c_hi);
-          for (int c = c_lo * 16; c < c_hi * 16; c += 16) {
-            float v[16];
-            tc::tmem_ld16(tbase + 256 + lane_base + c, v);
-            tc::tmem_wait_ld();
-            uint32_t hi[16], lo[16];
+        const int i = it.lin, N = D.dims[i + 1];
+        const uint8_t* abase = a.act_img + (tile * L + l) * tc_act_layer_bytes(D);
+        const uint32_t* himg =
+            reinterpret_cast<const uint32_t*>(abase + tc_act_item_off(D, i + 1) + (size_t)q * 2 * N * 128);
+        int c_lo, c_hi;
+        part(N / 16, c_lo, c_hi);
+        const int c0 = c_lo * 16, cn = (c_hi - c_lo) * 16;  // this thread's columns [c0, c0 + cn), cn <= 64
+        seg_base[0] = c0;
+        seg_len[0] = min(cn, 32);
+        seg_base[1] = c0 + 32;
+        seg_len[1] = max(0, cn - 32);
+        float v[64];
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4)
+          if (g4 * 16 < cn) tc::tmem_ld16(tbase + 256 + lane_base + c0 + g4 * 16, v + g4 * 16);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+          if (g4 * 16 < cn) {
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
-              const int o = tc::packed_b_offset(c + u, lane) >> 2;
+              const int c = c0 + g4 * 16 + u;
+              const int o = tc::packed_b_offset(c, lane) >> 2;
               const float hv = __uint_as_float(himg[o]) + __uint_as_float(himg[N * 32 + o]);
-              const float da = v[u] * (1.0f - hv * hv);
-              tc::split_tf32(da, hi[u], lo[u]);
-              T[(c + u) * BT_TS + t] = da;
+              T[c * BT_TS + t] = v[g4 * 16 + u] * (1.0f - hv * hv);
             }
-            tc::tmem_st8(t_ahi + lane_base + c, hi);
-            tc::tmem_st8(t_ahi + lane_base + c + 8, hi + 8);
-            tc::tmem_st8(t_alo + lane_base + c, lo);
-            tc::tmem_st8(t_alo + lane_base + c + 8, lo + 8);
           }
         }
-        run_item();  // dh_prev = da W_i  (acc 0; for i == 0: the conditioner-input gradient)
-        epi_bar();
-        S->bsum[hf][t] = write_transposed();
-        run_item();  // dW_i = da^T in_i   (acc 1)
-        {
-          const int Kin = D.dims[i];
-          stage_acc1(tc_pad16(Kin));
-          epi_bar();
-          for (int m = warp; m < N; m += TC_EPI_WARPS) {
-            float* dst = GL + D.off_W[i] + (int64_t)m * Kin;
-            if (i > 0) {
-              write_row(m, dst, Kin);  // hidden widths are multiples of 16: whole float4 columns
-            } else {
-              // first Linear: only the conditioning inputs ((j + l) odd) carry gradient; d need not be a multiple of 4
-              for (int c = lane; c < Kin; c += 32)
-                if (((c + l) & 1) == 1) acc_to(dst + c, T[m * BT_TS + c]);
-            }
-            if (lane == 0) acc_to(GL + D.off_b[i] + m, S->bsum[0][m] + S->bsum[1][m]);
-          }
-        }
-        epi_bar();
       }
-      // ---- masked coupling + ScalarAffine adjoints -------------------------------------------------
-      {
-        float ssc = 0.0f, ssh = 0.0f;
-        for (int c = (j_lo / 16) * 16; c < j_hi; c += 16) {
-          float v[16];
-          tc::tmem_ld16(tbase + 256 + lane_base + c, v);  // conditioner-input gradient (acc 0, N = pad16(d))
+    };
+    // dW tile of a finished unit (acc 1; lane = output unit m = t, columns = input units) -> this CTA's private
+    // accumulator, straight from tensor memory.  Inside the accumulator a weight block is stored PERMUTED,
+    // [column / 4][row][column % 4] (bt_private_to_canonical), so that the 32 lanes of a warp (32 consecutive
+    // rows) write 512 contiguous bytes per store; bt_reduce_kernel undoes the permutation while it sums.
+    auto reduce_unit = [&](int l, int ii) {
+      const int p = l & 1;
+      const BtItem it = PR.items[p][ii];
+      float* GL = PB + (int64_t)l * D.layer_stride;
+      int rows, ncols, ldc;  // rows per block, valid columns, canonical row length
+      float* blk;
+      bool active;
+      int64_t boff;
+      if (it.kind == BK_DG3) {
+        const int H = D.dims[nh];
+        const int f = p + 2 * (it.lin + q);  // warp q of each half owns feature slot q: rows q*32 .. q*32 + NP - 1
+        active = q < it.n_feat && lane < NP;
+        rows = NP; ncols = H; ldc = H;
+        blk = GL + D.off_W[nh] + (int64_t)f * NP * H + lane * 4;
+        boff = D.off_b[nh] + (int64_t)f * NP + lane;
+      } else {
+        const int i = it.lin;
+        rows = D.dims[i + 1]; ncols = D.dims[i]; ldc = ncols;
+        active = t < rows;
+        blk = GL + D.off_W[i] + t * 4;
+        boff = D.off_b[i] + t;
+      }
+      const bool permuted = (ncols & 3) == 0;
+      const int npad = tc_pad16(ncols);
+#pragma unroll 1
+      for (int g2 = 0; g2 < 2; ++g2) {
+        const int c0 = hf * 64 + g2 * 32;
+        if (c0 < npad) {
+          float v[32];
+          tc::tmem_ld16(tbase + 384 + lane_base + c0, v);
+          if (c0 + 16 < npad) tc::tmem_ld16(tbase + 384 + lane_base + c0 + 16, v + 16);
           tc::tmem_wait_ld();
+          if (active) {
+            if (permuted) {
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int j = c + u;
-            if (j >= j_lo && j < j_hi) {
-              float ga = gr[j];
-              if (((j + l) & 1) == 1) ga += v[u];
-              const float xa = (xin[j] + shift) * e;
-              if (valid) {
-                ssc += ga * xa;
-                ssh += ga * e;
-              }
-              gr[j] = ga * e;
+              for (int u = 0; u < 32; u += 4)
+                if (c0 + u < ncols) store4(blk + (int64_t)((c0 + u) >> 2) * rows * 4, v + u);
+            } else {
+              // first Linear with n_features not a multiple of 4: canonical layout, live (conditioning) columns only
+              float* dst = GL + D.off_W[it.lin] + (int64_t)t * ldc;
+#pragma unroll
+              for (int u = 0; u < 32; ++u)
+                if (c0 + u < ncols && ((c0 + u + l) & 1) == 1) acc_to(dst + c0 + u, v[u]);
             }
           }
         }
+      }
+      // bias gradient = row sum of dY^T (both halves of the tile's samples)
+      if (hf == 0 && active) acc_to(GL + boff, S->bsum[0][t] + S->bsum[1][t]);
+    };
+    // masked coupling + ScalarAffine adjoints of layer l (acc 0 holds the conditioner-input gradient)
+    auto finish_layer = [&](int l) {
+      const float* PL = P + (int64_t)l * D.layer_stride;
+      float* GL = PB + (int64_t)l * D.layer_stride;
+      const float shift = PL[D.off_shift], e = expf(PL[D.off_scale]);
+      const float* xin = a.save_x + ((int64_t)l * n + r) * d;
+      float ssc = 0.0f, ssh = 0.0f;
+      for (int c = (j_lo / 16) * 16; c < j_hi; c += 16) {
+        float v[16];
+        tc::tmem_ld16(tbase + 256 + lane_base + c, v);  // N = pad16(d) columns
+        tc::tmem_wait_ld();
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          ssc += __shfl_xor_sync(0xffffffffu, ssc, o);
-          ssh += __shfl_xor_sync(0xffffffffu, ssh, o);
-        }
-        if (lane == 0) {
-          S->red[warp] = ssc;
-          S->red[TC_EPI_WARPS + warp] = ssh;
-        }
-        epi_bar();
-        if (tid == 0) {
-          float sa = 0.0f, sb = 0.0f;
-          for (int w = 0; w < TC_EPI_WARPS; ++w) {
-            sa += S->red[w];
-            sb += S->red[TC_EPI_WARPS + w];
+        for (int u = 0; u < 16; ++u) {
+          const int j = c + u;
+          if (j >= j_lo && j < j_hi) {
+            float ga = gr[j];
+            if (((j + l) & 1) == 1) ga += v[u];
+            const float xa = (xin[j] + shift) * e;
+            if (valid) {
+              ssc += ga * xa;
+              ssh += ga * e;
+            }
+            gr[j] = ga * e;
           }
-          const int n_valid = (int)min((int64_t)TC_M, n - row0);
-          acc_to(GL + D.off_scale, sa - a.inv_n * (float)d * (float)n_valid);
-          acc_to(GL + D.off_shift, sb);
         }
-        epi_bar();
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ssc += __shfl_xor_sync(0xffffffffu, ssc, o);
+        ssh += __shfl_xor_sync(0xffffffffu, ssh, o);
+      }
+      if (lane == 0) {
+        S->red[warp] = ssc;
+        S->red[TC_EPI_WARPS + warp] = ssh;
+      }
+      epi_bar();
+      if (tid == 0) {
+        float sa = 0.0f, sb = 0.0f;
+        for (int w = 0; w < TC_EPI_WARPS; ++w) {
+          sa += S->red[w];
+          sb += S->red[TC_EPI_WARPS + w];
+        }
+        const int n_valid = (int)min((int64_t)TC_M, n - row0);
+        acc_to(GL + D.off_scale, sa - a.inv_n * (float)d * (float)n_valid);
+        acc_to(GL + D.off_shift, sb);
+      }
+      epi_bar();  // gr complete for the next layer
+    };
+
+    // One loop, one call site per stage; the iteration after the last unit only drains: it finishes the last
+    // layer and stores the last dW tile.
+    int l = L - 1, ii = 0, pl = -1, pii = 0;  // current unit; previous unit (its dW tile is still in acc 1)
+    while (true) {
+      const bool have = l >= 0;
+      if (pl >= 0 && (!have || l != pl)) finish_layer(pl);  // [F] layer boundary: needs the dgrad of the last unit
+      if (have) prepare(l, ii);                             // [F] overlaps the wgrad MMAs of the previous unit
+      BT_STAMP();
+      if (pl >= 0) wait_item();                             // [G] wgrad of the previous unit done
+      BT_STAMP();
+      if (have) {
+        write_arow();                                       // [A] -> dgrad MMAs start
+        arrive_item();
+      }
+      if (pl >= 0) reduce_unit(pl, pii);                    // [C] overlaps the dgrad MMAs
+      BT_STAMP();
+      if (!have) break;
+      wait_item();                                          // [D] dgrad done: the A region is free
+      epi_bar();                                            // T of this unit complete (long since), bsum consumed
+      BT_STAMP();
+      {                                                     // [E] dY^T: lane = output unit t, columns = the tile's rows
+        const float* src = T + t * BT_TS + hf * 64;
+        float bsum = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) {
+          const float4 v0 = *reinterpret_cast<const float4*>(src + c);
+          const float4 v1 = *reinterpret_cast<const float4*>(src + c + 4);
+          const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            bsum += v[u];
+            tc::split_tf32(v[u], hi[u], lo[u]);
+          }
+          tc::tmem_st8(t_ahi + lane_base + hf * 64 + c, hi);
+          tc::tmem_st8(t_alo + lane_base + hf * 64 + c, lo);
+        }
+        S->bsum[hf][t] = bsum;
+      }
+      arrive_item();                                        // -> wgrad MMAs start
+      epi_bar();                                            // T free for the next unit's prepare; bsum visible
+      BT_STAMP();
+      pl = l;
+      pii = ii;
+      ii += 2;
+      if (ii >= PR.n_items[l & 1]) {
+        --l;
+        ii = 0;
       }
     }
     }  // tiles
@@ -517,36 +570,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
   if (warp == TC_EPI_WARPS) tc::tmem_dealloc<512>(tbase);
 }
 
-// grad[i] = sum over CTAs of their private accumulators, in CTA order (deterministic).  Entries no CTA writes
-// (alignment padding, W3 / b3 rows of the features a layer does not transform, W1 columns of the masked inputs) are
-// recognised from the index and left at zero.
+// grad = sum over CTAs of their private accumulators, in CTA order (deterministic).  The accumulators are read in
+// their own (permuted) order -- coalesced, they are the bulk of the traffic -- and the sum is scattered to the
+// canonical position.  Entries no CTA writes (alignment padding, W3 / b3 rows of the features a layer does not
+// transform, W1 columns of the masked inputs) are recognised from the index and left at zero.
 __global__ void bt_reduce_kernel(const FlowmcFlowDesc D, const float* __restrict__ partial, int64_t pstride, int n_cta,
                                  float* __restrict__ grad, float* __restrict__ loss) {
   const int nh = D.n_linear - 1, NP = 3 * D.num_bins + 1, d = D.n_features;
   const int64_t total = (int64_t)D.n_layers * D.layer_stride;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int l = (int)(i / D.layer_stride);
-    const int64_t o = i - (int64_t)l * D.layer_stride;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+    const int l = (int)(j / D.layer_stride);
+    int64_t o = j - (int64_t)l * D.layer_stride;  // private offset inside the layer -> canonical offset
     bool live = false;
-    if (o >= D.off_W[nh] && o < D.off_W[nh] + (int64_t)D.dims[nh + 1] * D.dims[nh]) {
-      const int f = (int)((o - D.off_W[nh]) / D.dims[nh]) / NP;
+    const int H = D.dims[nh];
+    if (o >= D.off_W[nh] && o < D.off_W[nh] + (int64_t)D.dims[nh + 1] * H) {
+      const int jj = (int)(o - D.off_W[nh]);
+      const int f = jj / (NP * H), r2 = jj - f * NP * H;
+      const int c = (r2 / (4 * NP)) * 4 + (r2 & 3), rr = (r2 >> 2) % NP;
+      o = D.off_W[nh] + (int64_t)(f * NP + rr) * H + c;
       live = ((f ^ l) & 1) == 0;
     } else if (o >= D.off_b[nh] && o < D.off_b[nh] + D.dims[nh + 1]) {
       live = ((((int)(o - D.off_b[nh]) / NP) ^ l) & 1) == 0;
     } else if (o >= D.off_W[0] && o < D.off_W[0] + (int64_t)D.dims[1] * d) {
-      live = ((((int)((o - D.off_W[0]) % d)) + l) & 1) == 1;
+      int c;
+      if ((d & 3) == 0) {
+        const int jj = (int)(o - D.off_W[0]), N = D.dims[1];
+        c = (jj / (4 * N)) * 4 + (jj & 3);
+        o = D.off_W[0] + (int64_t)((jj >> 2) % N) * d + c;
+      } else {
+        c = (int)((o - D.off_W[0]) % d);
+      }
+      live = ((c + l) & 1) == 1;
     } else if (o == D.off_scale || o == D.off_shift) {
       live = true;
     } else {
       for (int k = 0; k < nh; ++k) {
-        if (k > 0 && o >= D.off_W[k] && o < D.off_W[k] + (int64_t)D.dims[k + 1] * D.dims[k]) live = true;
+        if (k > 0 && o >= D.off_W[k] && o < D.off_W[k] + (int64_t)D.dims[k + 1] * D.dims[k]) {
+          const int jj = (int)(o - D.off_W[k]), N = D.dims[k + 1];
+          o = D.off_W[k] + (int64_t)((jj >> 2) % N) * D.dims[k] + (jj / (4 * N)) * 4 + (jj & 3);
+          live = true;
+          break;
+        }
         if (o >= D.off_b[k] && o < D.off_b[k] + D.dims[k + 1]) live = true;
       }
     }
     if (live) {
       float s = 0.0f;
-      for (int c = 0; c < n_cta; ++c) s += partial[(int64_t)c * pstride + i];
-      grad[i] = s;
+      for (int c = 0; c < n_cta; ++c) s += partial[(int64_t)c * pstride + j];
+      grad[(int64_t)l * D.layer_stride + o] = s;
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
