@@ -105,7 +105,7 @@ __device__ __forceinline__ int64_t tc_layer_base(const FlowmcFlowDesc& D, const 
   return (int64_t)((l + 1) / 2) * P.layer_bytes[0] + (int64_t)(l / 2) * P.layer_bytes[1];
 }
 
-// blob -> packed image.  grid = (items, layers)
+// blob -> packed image.  grid = (items, layers, element slices)
 __global__ void tc_pack_flow_kernel(const FlowmcFlowDesc D, const TcProgram P, const float* __restrict__ params,
                                     uint8_t* __restrict__ image) {
   const int l = blockIdx.y, p = l & 1;
@@ -116,7 +116,7 @@ __global__ void tc_pack_flow_kernel(const FlowmcFlowDesc D, const TcProgram P, c
   float* dst = reinterpret_cast<float*>(image + tc_layer_base(D, P, l) + it.off);
   const int per_stage = it.npad * 32;
   const int total = it.n_kc * per_stage;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+  for (int i = blockIdx.z * blockDim.x + threadIdx.x; i < total; i += blockDim.x * gridDim.z) {
     const int kc = i / per_stage, rem = i - kc * per_stage;
     const int n = rem >> 5, kk = rem & 31;
     const int k = kc * 32 + kk;
@@ -691,7 +691,7 @@ int flowmc_flow_tc_pack(const FlowmcFlowDesc* D, const float* params, void* imag
   TcProgram PR;
   if (int rc = tc_build_program(*D, &PR)) return rc;
   const int items = PR.n_items[0] > PR.n_items[1] ? PR.n_items[0] : PR.n_items[1];
-  tc_pack_flow_kernel<<<dim3(items, D->n_layers), 256, 0, (cudaStream_t)stream>>>(*D, PR, params,
+  tc_pack_flow_kernel<<<dim3(items, D->n_layers, 8), 256, 0, (cudaStream_t)stream>>>(*D, PR, params,
                                                                                   static_cast<uint8_t*>(image));
   flowmc_count_launch();
   cudaError_t e = cudaGetLastError();

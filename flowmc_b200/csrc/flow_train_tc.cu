@@ -97,9 +97,11 @@ __host__ __device__ inline int64_t bt_layer_base(const BtProgram& P, int l) {
   return (int64_t)((l + 1) / 2) * P.layer_bytes[0] + (int64_t)(l / 2) * P.layer_bytes[1];
 }
 
-// transposed weight images for the data-gradient GEMMs.  grid = (items, layers)
+// transposed weight images for the data-gradient GEMMs.  grid = (items, layers, element slices)
 __global__ void bt_pack_kernel(const FlowmcFlowDesc D, const BtProgram P, const float* __restrict__ params,
-                               uint8_t* __restrict__ image) {
+                               uint8_t* __restrict__ image, int* __restrict__ done) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+    for (int i = threadIdx.x; i <= D.n_layers; i += blockDim.x) done[i] = 0;  // flags + work counter
   const int l = blockIdx.y, p = l & 1;
   if ((int)blockIdx.x >= P.n_items[p]) return;
   const BtItem it = P.items[p][blockIdx.x];
@@ -109,7 +111,7 @@ __global__ void bt_pack_kernel(const FlowmcFlowDesc D, const BtProgram P, const 
   float* dst = reinterpret_cast<float*>(image + bt_layer_base(P, l) + it.off);
   const int per_stage = it.N * 32;
   const int total = it.n_kc * per_stage;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+  for (int i = blockIdx.z * blockDim.x + threadIdx.x; i < total; i += blockDim.x * gridDim.z) {
     const int kc = i / per_stage, rem = i - kc * per_stage;
     const int n = rem >> 5, kk = rem & 31;
     float w = 0.0f;
@@ -146,12 +148,20 @@ struct BtArgs {
   int64_t pstride;     // floats per CTA: L * layer_stride + 4 (the last 4: loss partial)
   int64_t n_tiles;
   long long* timing;  // optional diagnostics: clock64 stamps of epilogue thread 0 of CTA 0
+  int n_cta;          // CTAs that process tiles; CTAs beyond them (if any) are REDUCERS, see bt_reduce_layer
+  int* done;          // [L] tile CTAs that have finished layer l (reducer hand-off) + [1] reduction work counter;
+                      // zeroed by bt_pack_kernel
 };
 
 #define BT_STAMP()                                                                                \
   do {                                                                                            \
     if (a.timing != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 256) a.timing[n_stamp++] = clock64(); \
   } while (0)
+
+__device__ __forceinline__ void bt_reduce_layer(const FlowmcFlowDesc& D, const float* partial, int64_t pstride,
+                                                int n_cta, float* __restrict__ grad, int l, int g0, int gstep,
+                                                int g_end);
+__device__ __forceinline__ float bt_reduce_loss(const float* partial, int64_t pstride, int n_cta);
 
 struct BtSmem {
   uint64_t stage_full[BT_STAGES], stage_empty[BT_STAGES], acc_full, a_ready;
@@ -164,6 +174,7 @@ template <int KB>
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const FlowmcFlowDesc D, const BtProgram PR,
                                                                          const BtArgs a) {
   constexpr int NP = 3 * KB + 1;
+  if ((int)blockIdx.x < a.n_cta) {  // ===== tile CTA (CTAs beyond n_cta only reduce, below) =====
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stages = smem;
@@ -196,7 +207,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
   if (warp == TC_EPI_WARPS) {
     // ===== B-stage producer ====================================================================
     uint32_t s = 0, ph = 0;
-    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
+    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += a.n_cta)
     for (int l = L - 1; l >= 0; --l) {
       const int p = l & 1;
       const uint8_t* wbase = a.wimg + bt_layer_base(PR, l);
@@ -219,7 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
   } else if (warp == TC_EPI_WARPS + 1) {
     // ===== MMA issuer ==========================================================================
     uint32_t s = 0, ph = 0, a_ph = 0;
-    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x)
+    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += a.n_cta)
     for (int l = L - 1; l >= 0; --l) {
       const int p = l & 1;
       for (int ii = 0; ii < PR.n_items[p]; ++ii) {
@@ -314,8 +325,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
         }
       }
     };
-    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += a.n_cta) {
     const bool first = tile == (int64_t)blockIdx.x;  // first tile of this CTA: store, later tiles: accumulate
+    const bool last = tile + a.n_cta >= a.n_tiles;   // last tile: publish the layers to the reducers
     auto acc_to = [&](float* ptr, float v) { *ptr = first ? v : *ptr + v; };
     auto store4 = [&](float* ptr, const float* v) {
       float4 w = make_float4(v[0], v[1], v[2], v[3]);
@@ -390,22 +402,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
         seg_len[0] = min(cn, 32);
         seg_base[1] = c0 + 32;
         seg_len[1] = max(0, cn - 32);
-        float v[64];
+        // 16 columns at a time; the activation words of the next group are requested before this group's are
+        // consumed (the image comes from L2 / HBM: ~1 us away)
+        uint32_t hb[2][32];
+        auto request = [&](int g4, uint32_t* dst) {
 #pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4)
-          if (g4 * 16 < cn) tc::tmem_ld16(tbase + 256 + lane_base + c0 + g4 * 16, v + g4 * 16);
-        tc::tmem_wait_ld();
+          for (int u = 0; u < 16; ++u) {
+            const int o = tc::packed_b_offset(c0 + g4 * 16 + u, lane) >> 2;
+            dst[u] = __ldg(himg + o);
+            dst[16 + u] = __ldg(himg + N * 32 + o);
+          }
+        };
+        if (cn > 0) request(0, hb[0]);
 #pragma unroll
         for (int g4 = 0; g4 < 4; ++g4) {
           if (g4 * 16 < cn) {
+            if ((g4 + 1) * 16 < cn) request(g4 + 1, hb[(g4 + 1) & 1]);
+            float v[16];
+            tc::tmem_ld16(tbase + 256 + lane_base + c0 + g4 * 16, v);
+            tc::tmem_wait_ld();
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
-              const int c = c0 + g4 * 16 + u;
-              const int o = tc::packed_b_offset(c, lane) >> 2;
-              const float hv = __uint_as_float(himg[o]) + __uint_as_float(himg[N * 32 + o]);
-              T[c * BT_TS + t] = v[g4 * 16 + u] * (1.0f - hv * hv);
+              const float hv = __uint_as_float(hb[g4 & 1][u]) + __uint_as_float(hb[g4 & 1][16 + u]);
+              T[(c0 + g4 * 16 + u) * BT_TS + t] = v[u] * (1.0f - hv * hv);
             }
           }
+        }
+      }
+    };
+    // the unit after (l, ii): pull the spline parameters its prepare() will read (HBM, written by the forward pass)
+    // into L2 one unit ahead
+    auto prefetch_next = [&](int l, int ii) {
+      int nl = l, nii = ii + 2;
+      if (nii >= PR.n_items[l & 1]) { --nl; nii = 0; }
+      if (nl < 0) return;
+      const BtItem it = PR.items[nl & 1][nii];
+      if (it.kind != BK_DG3) return;
+      int i_lo, i_hi;
+      part(it.n_feat, i_lo, i_hi);
+      for (int fi = i_lo; fi < i_hi; ++fi) {
+        const float* th = a.save_theta + ((int64_t)nl * ((d + 1) / 2) + it.lin + fi) * NP * n + r;
+        if (lane == 0) {  // one request per 128-byte line (the warp's 32 rows)
+#pragma unroll
+          for (int u = 0; u < NP; ++u) asm volatile("prefetch.global.L2 [%0];" ::"l"(th + (int64_t)u * n));
         }
       }
     };
@@ -525,8 +564,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
       if (have) {
         write_arow();                                       // [A] -> dgrad MMAs start
         arrive_item();
+        prefetch_next(l, ii);
       }
       if (pl >= 0) reduce_unit(pl, pii);                    // [C] overlaps the dgrad MMAs
+      if (last && a.done != nullptr && pl >= 0 && (!have || l != pl)) {
+        // layer pl of this CTA's accumulator is final: publish it to the reducer CTAs
+        __threadfence();
+        epi_bar();
+        if (tid == 0) atomicAdd(a.done + pl, 1);
+      }
       BT_STAMP();
       if (!have) break;
       wait_item();                                          // [D] dgrad done: the A region is free
@@ -568,63 +614,159 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
   __syncthreads();
   tc::tc_fence_after();
   if (warp == TC_EPI_WARPS) tc::tmem_dealloc<512>(tbase);
+  }  // tile CTA
+  if (a.done == nullptr) return;  // reduction by bt_reduce_kernel
+
+  // ===== in-kernel reduction of the private accumulators ==============================================
+  // The CTAs beyond n_cta (SMs the tiles leave idle) start here at once; the tile CTAs join when their tiles are
+  // done.  Work = (layer, slice of the layer) chunks handed out in order L-1 .. 0 through an atomic counter; a chunk
+  // of layer l can start as soon as every tile CTA has published that layer (a.done[l]): the sum over the accumulators
+  // -- still in L2 -- overlaps the backward pass of the layers below, and only the tail runs on all SMs.  The
+  // order of the sum inside an element is fixed (CTA order), whoever computes it.
+  {
+    __shared__ int s_chunk;
+    const int Lr = D.n_layers;
+    const int n_groups = (int)(D.layer_stride >> 2);
+    const int gpc = 2 * (int)blockDim.x;
+    const int per_layer = (n_groups + gpc - 1) / gpc;
+    for (;;) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int c = atomicAdd(a.done + Lr, 1);
+        if (c < Lr * per_layer) {
+          const int* flag = a.done + (Lr - 1 - c / per_layer);
+          int v;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v < a.n_cta) __nanosleep(128);
+          } while (v < a.n_cta);
+        }
+        s_chunk = c;
+      }
+      __syncthreads();
+      const int c = s_chunk;
+      if (c >= Lr * per_layer) break;
+      const int l = Lr - 1 - c / per_layer, ch = c % per_layer;
+      bt_reduce_layer(D, a.partial, a.pstride, a.n_cta, a.grad, l, ch * gpc + (int)threadIdx.x, (int)blockDim.x,
+                      min(n_groups, (ch + 1) * gpc));
+      if (c == Lr * per_layer - 1 && threadIdx.x == 0) *a.loss = bt_reduce_loss(a.partial, a.pstride, a.n_cta);
+    }
+  }
 }
 
 // grad = sum over CTAs of their private accumulators, in CTA order (deterministic).  The accumulators are read in
-// their own (permuted) order -- coalesced, they are the bulk of the traffic -- and the sum is scattered to the
-// canonical position.  Entries no CTA writes (alignment padding, W3 / b3 rows of the features a layer does not
+// their own (permuted) order, four consecutive floats per thread -- coalesced 16-byte loads, they are the bulk of the
+// traffic -- and the sum goes to the canonical position (a permuted group of four is four consecutive columns of one
+// canonical row).  Entries no CTA writes (alignment padding, W3 / b3 rows of the features a layer does not
 // transform, W1 columns of the masked inputs) are recognised from the index and left at zero.
-__global__ void bt_reduce_kernel(const FlowmcFlowDesc D, const float* __restrict__ partial, int64_t pstride, int n_cta,
-                                 float* __restrict__ grad, float* __restrict__ loss) {
+// Reduces the groups g = g0, g0 + gstep, ... < g_end of layer l.
+__device__ __forceinline__ void bt_reduce_layer(const FlowmcFlowDesc& D, const float* partial, int64_t pstride,
+                                                int n_cta, float* __restrict__ grad, int l, int g0, int gstep,
+                                                int g_end) {
   const int nh = D.n_linear - 1, NP = 3 * D.num_bins + 1, d = D.n_features;
-  const int64_t total = (int64_t)D.n_layers * D.layer_stride;
-  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
-    const int l = (int)(j / D.layer_stride);
-    int64_t o = j - (int64_t)l * D.layer_stride;  // private offset inside the layer -> canonical offset
-    bool live = false;
-    const int H = D.dims[nh];
-    if (o >= D.off_W[nh] && o < D.off_W[nh] + (int64_t)D.dims[nh + 1] * H) {
-      const int jj = (int)(o - D.off_W[nh]);
+  const int H = D.dims[nh];
+  const bool w0_permuted = (d & 3) == 0;
+  for (int g = g0; g < g_end; g += gstep) {
+    const int64_t jo = (int64_t)g * 4;  // private offset inside the layer
+    int64_t o = jo;                     // canonical offset of the group's first element
+    bool live[4] = {false, false, false, false};
+    if (jo >= D.off_W[nh] && jo < D.off_W[nh] + (int64_t)D.dims[nh + 1] * H) {
+      const int jj = (int)(jo - D.off_W[nh]);
       const int f = jj / (NP * H), r2 = jj - f * NP * H;
-      const int c = (r2 / (4 * NP)) * 4 + (r2 & 3), rr = (r2 >> 2) % NP;
+      const int c = (r2 / (4 * NP)) * 4, rr = (r2 >> 2) % NP;
       o = D.off_W[nh] + (int64_t)(f * NP + rr) * H + c;
-      live = ((f ^ l) & 1) == 0;
-    } else if (o >= D.off_b[nh] && o < D.off_b[nh] + D.dims[nh + 1]) {
-      live = ((((int)(o - D.off_b[nh]) / NP) ^ l) & 1) == 0;
-    } else if (o >= D.off_W[0] && o < D.off_W[0] + (int64_t)D.dims[1] * d) {
-      int c;
-      if ((d & 3) == 0) {
-        const int jj = (int)(o - D.off_W[0]), N = D.dims[1];
-        c = (jj / (4 * N)) * 4 + (jj & 3);
+      live[0] = live[1] = live[2] = live[3] = ((f ^ l) & 1) == 0;
+    } else if (jo >= D.off_W[0] && jo < D.off_W[0] + (int64_t)D.dims[1] * d) {
+      if (w0_permuted) {
+        const int jj = (int)(jo - D.off_W[0]), N = D.dims[1];
+        const int c = (jj / (4 * N)) * 4;
         o = D.off_W[0] + (int64_t)((jj >> 2) % N) * d + c;
+        live[0] = live[2] = ((c + l) & 1) == 1;
+        live[1] = live[3] = !live[0];
       } else {
-        c = (int)((o - D.off_W[0]) % d);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          live[e] = jo + e < D.off_W[0] + (int64_t)D.dims[1] * d && ((((int)((jo + e - D.off_W[0]) % d)) + l) & 1) == 1;
       }
-      live = ((c + l) & 1) == 1;
-    } else if (o == D.off_scale || o == D.off_shift) {
-      live = true;
     } else {
-      for (int k = 0; k < nh; ++k) {
-        if (k > 0 && o >= D.off_W[k] && o < D.off_W[k] + (int64_t)D.dims[k + 1] * D.dims[k]) {
-          const int jj = (int)(o - D.off_W[k]), N = D.dims[k + 1];
-          o = D.off_W[k] + (int64_t)((jj >> 2) % N) * D.dims[k] + (jj / (4 * N)) * 4 + (jj & 3);
-          live = true;
+      bool found = false;
+      for (int k = 1; k < nh; ++k) {
+        if (jo >= D.off_W[k] && jo < D.off_W[k] + (int64_t)D.dims[k + 1] * D.dims[k]) {
+          const int jj = (int)(jo - D.off_W[k]), N = D.dims[k + 1];
+          o = D.off_W[k] + (int64_t)((jj >> 2) % N) * D.dims[k] + (jj / (4 * N)) * 4;
+          live[0] = live[1] = live[2] = live[3] = true;
+          found = true;
           break;
         }
-        if (o >= D.off_b[k] && o < D.off_b[k] + D.dims[k + 1]) live = true;
+      }
+      if (!found) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int64_t oe = jo + e;
+          if (oe >= D.off_b[nh] && oe < D.off_b[nh] + D.dims[nh + 1]) {
+            live[e] = ((((int)(oe - D.off_b[nh]) / NP) ^ l) & 1) == 0;
+          } else if (oe == D.off_scale || oe == D.off_shift) {
+            live[e] = true;
+          } else {
+            for (int k = 0; k < nh; ++k)
+              if (oe >= D.off_b[k] && oe < D.off_b[k] + D.dims[k + 1]) live[e] = true;
+          }
+        }
       }
     }
-    if (live) {
-      float s = 0.0f;
-      for (int c = 0; c < n_cta; ++c) s += partial[(int64_t)c * pstride + j];
-      grad[(int64_t)l * D.layer_stride + o] = s;
+    if (live[0] | live[1] | live[2] | live[3]) {
+      const float4* src = reinterpret_cast<const float4*>(partial + (int64_t)l * D.layer_stride + jo);
+      const int64_t step4 = pstride >> 2;
+      float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      int c = 0;
+      for (; c + 16 <= n_cta; c += 16) {  // 16 independent 16-byte loads in flight, summed in CTA order
+        float4 v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (int64_t)(c + u) * step4);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+      }
+      for (; c < n_cta; ++c) {
+        const float4 v = __ldcg(src + (int64_t)c * step4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      float* dst = grad + (int64_t)l * D.layer_stride + o;
+      if (live[0] & live[1] & live[2] & live[3]) {
+        *reinterpret_cast<float4*>(dst) = s;
+      } else {
+        if (live[0]) dst[0] = s.x;
+        if (live[1]) dst[1] = s.y;
+        if (live[2]) dst[2] = s.z;
+        if (live[3]) dst[3] = s.w;
+      }
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    float s = 0.0f;
-    for (int c = 0; c < n_cta; ++c) s += partial[(int64_t)c * pstride + pstride - 4];
-    *loss = s;
+}
+
+__device__ __forceinline__ float bt_reduce_loss(const float* partial, int64_t pstride, int n_cta) {
+  float s = 0.0f;
+  for (int c = 0; c < n_cta; ++c) s += __ldcg(partial + (int64_t)c * pstride + pstride - 4);
+  return s;
+}
+
+// stand-alone reduction (used when the backward kernel has no spare SMs for in-kernel reducers)
+__global__ void bt_reduce_kernel(const FlowmcFlowDesc D, const float* __restrict__ partial, int64_t pstride, int n_cta,
+                                 float* __restrict__ grad, float* __restrict__ loss) {
+  for (int l = blockIdx.y; l < D.n_layers; l += gridDim.y)
+    bt_reduce_layer(D, partial, pstride, n_cta, grad, l, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x,
+                    (int)(D.layer_stride >> 2));
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *loss = bt_reduce_loss(partial, pstride, n_cta);
+}
+
+static int bt_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = BT_MAX_CTAS;
+    if (sms > BT_MAX_CTAS) sms = BT_MAX_CTAS;
   }
+  return sms;
 }
 
 template <int KB>
@@ -640,11 +782,20 @@ static int launch_bt(const FlowmcFlowDesc& D, const BtProgram& PR, const BtArgs&
     }
     configured = bytes;
   }
-  const int n_cta = (int)(a.n_tiles < BT_MAX_CTAS ? a.n_tiles : BT_MAX_CTAS);
-  kern<<<n_cta, TC_THREADS, bytes, stream>>>(D, PR, a);
+  // Spare SMs (fewer tiles than SMs) become in-kernel reducers: the sum over the private accumulators then overlaps
+  // the backward pass instead of following it.  All CTAs are co-resident (one per SM), so the reducers' spin-wait on
+  // the tile CTAs cannot starve them.
+  BtArgs b = a;
+  b.n_cta = (int)(a.n_tiles < BT_MAX_CTAS ? a.n_tiles : BT_MAX_CTAS);
+  const int n_red = bt_sm_count() - b.n_cta;
+  const bool fused = n_red >= 8;
+  if (!fused) b.done = nullptr;
+  kern<<<b.n_cta + (fused ? n_red : 0), TC_THREADS, bytes, stream>>>(D, PR, b);
   flowmc_count_launch();
-  bt_reduce_kernel<<<148 * 4, 256, 0, stream>>>(D, a.partial, a.pstride, n_cta, a.grad, a.loss);
-  flowmc_count_launch();
+  if (!fused) {
+    bt_reduce_kernel<<<dim3(32, D.n_layers), 256, 0, stream>>>(D, b.partial, b.pstride, b.n_cta, b.grad, b.loss);
+    flowmc_count_launch();
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     flowmc_set_error(cudaGetErrorString(e));
@@ -659,7 +810,7 @@ void flow_backward_tc_set_timing(long long* buf) { g_bt_timing = buf; }
 bool flow_backward_tc_supported(const FlowmcFlowDesc& D) {
   if (!tc_supported(D)) return false;
   if (D.num_bins == 16) return false;  // 49 parameters per feature do not fit the 32-column A slot
-  const size_t bytes = 2048 + (size_t)BT_STAGES * TC_STAGE_BYTES + (size_t)128 * BT_TS * 4 +
+  const size_t bytes = 4096 + (size_t)BT_STAGES * TC_STAGE_BYTES + (size_t)128 * BT_TS * 4 +
                        (size_t)TC_M * (D.n_features + 1) * 4;
   return bytes <= 227 * 1024;
 }
@@ -678,7 +829,8 @@ int64_t flow_backward_tc_act_bytes(const FlowmcFlowDesc& D, int64_t n) {
 
 int64_t flow_backward_tc_partial_bytes(const FlowmcFlowDesc& D, int64_t n) {
   const int64_t tiles = (n + TC_M - 1) / TC_M;
-  return (tiles < BT_MAX_CTAS ? tiles : BT_MAX_CTAS) * ((int64_t)D.n_layers * D.layer_stride + 4) * 4;
+  return (tiles < BT_MAX_CTAS ? tiles : BT_MAX_CTAS) * ((int64_t)D.n_layers * D.layer_stride + 4) * 4 +
+         (int64_t)(D.n_layers + 4) * 4;  // + the per-layer hand-off counters
 }
 
 int flow_backward_tc(const FlowmcFlowDesc& D, const float* params, uint8_t* wimg, const uint8_t* act_img,
@@ -687,12 +839,15 @@ int flow_backward_tc(const FlowmcFlowDesc& D, const float* params, uint8_t* wimg
   BtProgram PR;
   if (int rc = bt_build_program(D, &PR)) return rc;
   const int items = PR.n_items[0] > PR.n_items[1] ? PR.n_items[0] : PR.n_items[1];
-  bt_pack_kernel<<<dim3(items, D.n_layers), 256, 0, stream>>>(D, PR, params, wimg);
+  const int64_t tiles = (n + TC_M - 1) / TC_M;
+  const int64_t pstride = (int64_t)D.n_layers * D.layer_stride + 4;
+  int* done = reinterpret_cast<int*>(partial + (tiles < BT_MAX_CTAS ? tiles : BT_MAX_CTAS) * pstride);
+  bt_pack_kernel<<<dim3(items, D.n_layers, 8), 256, 0, stream>>>(D, PR, params, wimg, done);
   flowmc_count_launch();
   BtArgs a;
   a.params = params; a.wimg = wimg; a.act_img = act_img; a.save_x = save_x; a.save_theta = save_theta; a.logp = logp;
   a.n = n; a.inv_n = inv_n; a.grad = grad; a.loss = loss; a.timing = g_bt_timing;
-  a.partial = partial; a.pstride = (int64_t)D.n_layers * D.layer_stride + 4; a.n_tiles = (n + TC_M - 1) / TC_M;
+  a.partial = partial; a.pstride = pstride; a.n_tiles = tiles; a.done = done; a.n_cta = 0;
   switch (D.num_bins) {
     case 4: return launch_bt<4>(D, PR, a, stream);
     case 8: return launch_bt<8>(D, PR, a, stream);
