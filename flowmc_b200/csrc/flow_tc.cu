@@ -21,6 +21,7 @@
 //     warps per scheduler hide the MUFU / TMEM latencies of the spline chains), warp 16 weight producer (one elected
 //     lane issues the bulk copies), warp 17 MMA issuer (one elected lane).
 //   TMEM map (512 columns): [0,128) A hi | [128,256) A lo | [256,384) acc slot 0 | [384,512) acc slot 1.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -162,6 +163,7 @@ struct TcArgs {
   float* save_theta;  // [L][ceil(d/2) * NP][n]   spline parameters (bias included) of the transformed features
   uint8_t* act_img;   // per (tile, layer): conditioner input and hidden activations as packed B stages (K = the
                       // tile's 128 rows) for the tensor-core weight-gradient GEMMs (flow_tc.cuh: tc_act_*)
+  int act_staged;     // act_img blocks go through a per-warp shared-memory buffer + bulk stores (the buffer fits)
   long long* timing;  // optional diagnostics: [3][256] clock64 stamps of CTA 0 (producer, MMA issuer, epilogue thread 0)
 };
 
@@ -171,7 +173,9 @@ struct TcArgs {
   } while (0)
 
 struct TcSmem {
-  uint64_t stage_full[TC_STAGES], stage_empty[TC_STAGES], acc_full[2], acc_empty[2], a_ready;
+  uint64_t stage_full[TC_STAGES], stage_empty[TC_STAGES], acc_full[2], acc_empty[2];
+  uint64_t a_ready[4];  // per K-chunk (32 columns) of the A operand: a GEMM starts on the first chunk while the
+                        // epilogue threads are still writing the later ones
   uint32_t tmem_base;
   float ldpart[TC_PARTS][TC_M];
 };
@@ -193,11 +197,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
   float* sbias_all = xs + TC_M * xs_stride;
   const int bias_stride = (D.n_linear - 1) * 128 + ((d + 1) / 2) * NP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // training only: per-warp staging of the activation-image blocks, [hi: 8 rows x 128 B][lo: 8 rows x 128 B]
+  uint8_t* astage_all = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(sbias_all + D.n_layers * bias_stride) + 127) & ~(uintptr_t)127);
   const float* P = a.params;
   const int L = D.n_layers, nh = D.n_linear - 1;
   const int n_pass = (MODE == TC_NF) ? 2 : 1;
   const int64_t row0 = (int64_t)blockIdx.x * TC_M;
-
   if (warp == TC_EPI_WARPS + 1 && lane == 0) {
     for (int i = 0; i < TC_STAGES; ++i) {
       tc::mbar_init(&S->stage_full[i], 1);
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
       tc::mbar_init(&S->acc_full[i], 1);
       tc::mbar_init(&S->acc_empty[i], TC_EPI);
     }
-    tc::mbar_init(&S->a_ready, TC_EPI);
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&S->a_ready[i], TC_EPI);
     tc::fence_mbar_init();
   }
   if (warp == TC_EPI_WARPS) tc::tmem_alloc<512>(&S->tmem_base);
@@ -256,10 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
           const int l = inv ? L - 1 - li : li, p = l & 1;
           for (int ii = 0; ii < PR.n_items[p]; ++ii) {
             const TcItem it = PR.items[p][ii];
-            if (it.kind == 0 || it.lin == 0) {  // a new A operand: masked x, h1, ..., h_last
-              tc::mbar_wait(&S->a_ready, a_ph);
-              a_ph ^= 1;
-            }
+            const bool new_a = it.kind == 0 || it.lin == 0;  // a new A operand: masked x, h1, ..., h_last
             const uint32_t slot = seq & 1;
             tc::mbar_wait(&S->acc_empty[slot], ((seq >> 1) & 1) ^ 1);
             tc::tc_fence_after();
@@ -268,6 +271,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
             const uint32_t idesc = tc::make_idesc_tf32(TC_M, it.npad);
             const bool three = a.terms == 3;
             for (int kc = 0; kc < it.n_kc; ++kc) {
+              if (new_a) {  // K-chunk kc of the operand has been written
+                tc::mbar_wait(&S->a_ready[kc], (a_ph >> kc) & 1);
+                a_ph ^= 1u << kc;
+              }
               tc::mbar_wait(&S->stage_full[s], ph);
               tc::tc_fence_after();
               if (kc == 0 && lane == 0) TC_STAMP(1);  // first weight stage landed
@@ -313,6 +320,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     const int64_t grow = row0 + row;
     const int64_t r = min(grow, a.n - 1);
     float* xr = xs + row * xs_stride;
+    // Activation image block of 8 operand columns n0 .. n0 + 7 (= 8 image rows of 128 B: this warp's 32 samples)
+    // -> global.  Staged: the 32 lanes write their words into the warp's shared-memory buffer in image order and one
+    // lane sends the two 1 KB blocks with bulk stores (asynchronous, full lines) instead of 16 scattered 4-byte
+    // stores per thread.
+    uint8_t* astage = astage_all + warp * 2048;
+    auto dump_block8 = [&](const uint32_t* hi8, const uint32_t* lo8, int n0, uint8_t* gimg, int n_rows) {
+      if (a.act_staged) {
+        if (lane == 0) tc::bulk_wait_read<0>();  // the previous block has left the buffer
+        __syncwarp();
+        uint32_t* st = reinterpret_cast<uint32_t*>(astage);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int o = tc::packed_b_offset(u, lane) >> 2;
+          st[o] = hi8[u];
+          st[256 + o] = lo8[u];
+        }
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tc::bulk_s2g(gimg + (size_t)n0 * 128, astage, 1024);
+          tc::bulk_s2g(gimg + (size_t)(n_rows + n0) * 128, astage + 1024, 1024);
+          tc::bulk_commit();
+        }
+      } else {
+        uint32_t* img = reinterpret_cast<uint32_t*>(gimg);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int o = tc::packed_b_offset(n0 + u, lane) >> 2;
+          img[o] = hi8[u];
+          img[n_rows * 32 + o] = lo8[u];
+        }
+      }
+    };
     // this thread's share of the d features (affine / operand writes / pre / post): 8-column groups
     const int g_all = (d + 7) >> 3;
     int g_lo, g_hi;
@@ -381,10 +421,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
         }
       }
     }
+    // the tile (all rows, complete after an epi_bar) -> save_x[slot]: rows are contiguous in global memory, so the
+    // CTA writes them as one coalesced stream
+    auto save_tile = [&](int slot) {
+      const int64_t rows = min((int64_t)TC_M, a.n - row0);
+      float* dst = a.save_x + ((int64_t)slot * a.n + row0) * d;
+      for (int e = tid; e < (int)rows * d; e += TC_EPI) {
+        const int rr = e / d;
+        dst[e] = xs[rr * xs_stride + (e - rr * d)];
+      }
+    };
     float ldacc = 0.0f;
     uint32_t seq = 0;
     int n_stamp = (tid == 0) ? 0 : 256;
     TC_STAMP(2);  // tile loaded
+    if (MODE == TC_TRAIN) epi_bar();  // save_tile(0) reads every thread's part of the tile
 
     for (int pass = 0; pass < n_pass; ++pass) {
       const bool inv = (MODE == TC_INV) || (MODE == TC_NF && pass == 0);
@@ -393,8 +444,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
         const float* PL = P + (int64_t)l * D.layer_stride;
         const float scale = PL[D.off_scale], shift = PL[D.off_shift];
         const float* sbias = sbias_all + l * bias_stride;
-        if (MODE == TC_TRAIN && a.save_x != nullptr && grow < a.n)
-          for (int j = j_lo; j < j_hi; ++j) a.save_x[((int64_t)l * a.n + grow) * d + j] = xr[j];
+        if (MODE == TC_TRAIN && a.save_x != nullptr) {
+          save_tile(l);
+          epi_bar();  // the affine below rewrites the tile
+        }
         // ---- ScalarAffine (rqSpline.py:435-436) + A operand = x * mask, hi / lo ------------------
         {
           const float e = inv ? expf(-scale) : expf(scale);
@@ -416,20 +469,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
             tc::tmem_st8(t_alo + lane_base + g * 8, lo);
             if (MODE == TC_TRAIN && a.act_img != nullptr) {
               const int npx = tc_pad16(d);
-              uint32_t* img = reinterpret_cast<uint32_t*>(a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) +
-                                                          (size_t)q * 2 * npx * 128);
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const int o = tc::packed_b_offset(g * 8 + u, lane) >> 2;
-                img[o] = hi[u];
-                img[npx * 32 + o] = lo[u];
-              }
+              dump_block8(hi, lo, g * 8,
+                          a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) + (size_t)q * 2 * npx * 128, npx);
             }
           }
           if (hf == 0) ldacc += inv ? -(float)d * scale : (float)d * scale;
           tc::tmem_wait_st();
           tc::tc_fence_before();
-          tc::mbar_arrive(&S->a_ready);
+          for (int kc = 0; kc < PR.items[p][0].n_kc; ++kc) tc::mbar_arrive(&S->a_ready[kc]);
           epi_bar();  // the row's other thread reads these x values in the spline stage
           TC_STAMP(2);  // affine + operand written
         }
@@ -442,43 +489,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
           TC_STAMP(2);  // accumulator observed full
           if (it.kind == 0) {
             // ---- tanh(acc + b) -> next A operand (this thread: half of the columns) ----------------
+            // Columns in 16-wide groups, interleaved between the row's two threads (group 2 j + hf), so that K-chunk j
+            // (32 columns) of the next GEMM's operand is complete after step j and its MMAs start while the later
+            // columns are still being computed.
+            static_assert(TC_PARTS == 2, "column interleave assumes two threads per row");
             const int N = it.npad;               // hidden width, multiple of 16
-            int c_lo, c_hi;
-            part(N / 16, c_lo, c_hi);
-            c_lo *= 16;
-            c_hi *= 16;
             const float* bias = sbias + it.lin * 128;
-            for (int c = c_lo; c < c_hi; c += 16) {
-              float v[16];
-              tc::tmem_ld16(t_acc + c, v);
-              tc::tmem_wait_ld();
-              uint32_t hi[16], lo[16];
-#pragma unroll
-              for (int u = 0; u < 16; ++u) {
-                const float hv = tanh_ex2(v[u] + bias[c + u]);
-                tc::split_tf32(hv, hi[u], lo[u]);
-                if (MODE == TC_TRAIN && a.save_h != nullptr && grow < a.n)
-                  a.save_h[((int64_t)(l * nh + it.lin) * 128 + c + u) * a.n + grow] = hv;
-              }
-              if (MODE == TC_TRAIN && a.act_img != nullptr) {
-                uint32_t* img = reinterpret_cast<uint32_t*>(a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) +
-                                                            tc_act_item_off(D, it.lin + 1) + (size_t)q * 2 * N * 128);
+            for (int j = 0; j < (N + 31) / 32; ++j) {
+              const int c = (2 * j + hf) * 16;
+              if (c < N) {
+                float v[16];
+                tc::tmem_ld16(t_acc + c, v);
+                tc::tmem_wait_ld();
+                uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
-                  const int o = tc::packed_b_offset(c + u, lane) >> 2;
-                  img[o] = hi[u];
-                  img[N * 32 + o] = lo[u];
+                  const float hv = tanh_ex2(v[u] + bias[c + u]);
+                  tc::split_tf32(hv, hi[u], lo[u]);
+                  if (MODE == TC_TRAIN && a.save_h != nullptr && grow < a.n)
+                    a.save_h[((int64_t)(l * nh + it.lin) * 128 + c + u) * a.n + grow] = hv;
                 }
+                if (MODE == TC_TRAIN && a.act_img != nullptr) {
+                  uint8_t* gimg = a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) +
+                                  tc_act_item_off(D, it.lin + 1) + (size_t)q * 2 * N * 128;
+                  dump_block8(hi, lo, c, gimg, N);
+                  dump_block8(hi + 8, lo + 8, c + 8, gimg, N);
+                }
+                tc::tmem_st8(t_ahi + lane_base + c, hi);
+                tc::tmem_st8(t_ahi + lane_base + c + 8, hi + 8);
+                tc::tmem_st8(t_alo + lane_base + c, lo);
+                tc::tmem_st8(t_alo + lane_base + c + 8, lo + 8);
+                tc::tmem_wait_st();
               }
-              tc::tmem_st8(t_ahi + lane_base + c, hi);
-              tc::tmem_st8(t_ahi + lane_base + c + 8, hi + 8);
-              tc::tmem_st8(t_alo + lane_base + c, lo);
-              tc::tmem_st8(t_alo + lane_base + c + 8, lo + 8);
+              tc::tc_fence_before();
+              tc::mbar_arrive(&S->a_ready[j]);
             }
-            tc::tmem_wait_st();
-            tc::tc_fence_before();
             tc::mbar_arrive(&S->acc_empty[slot]);
-            tc::mbar_arrive(&S->a_ready);
           } else {
             // ---- spline epilogue: this thread's half of the chunk's features ------------------------
             const int nf = it.n_feat;
@@ -551,8 +597,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     }
 
     // ---- epilogue of the tile ------------------------------------------------------------------
-    if (MODE == TC_TRAIN && a.save_x != nullptr && grow < a.n)
-      for (int j = j_lo; j < j_hi; ++j) a.save_x[((int64_t)L * a.n + grow) * d + j] = xr[j];
+    if (MODE == TC_TRAIN && a.save_x != nullptr) save_tile(L);  // (the layer loop ended with an epi_bar)
     S->ldpart[hf][row] = ldacc;
     epi_bar();
     const int post = (MODE == TC_NF) ? POST_BASE_LOGP : a.post;
@@ -578,6 +623,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
         }
       }
     }
+    if (MODE == TC_TRAIN && a.act_staged && lane == 0) tc::bulk_wait<0>();  // this lane's bulk stores have landed
     tc::tc_fence_before();
   }
   __syncthreads();
@@ -588,10 +634,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
 template <int KB, int MODE>
 static int launch_tc(const FlowmcFlowDesc& D, const TcProgram& PR, const TcArgs& a, cudaStream_t stream) {
   auto kern = flow_tc_kernel<KB, MODE>;
-  const size_t bytes = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + ((sizeof(TcSmem) + 15) & ~15) +
-                       (size_t)TC_M * (D.n_features + 1) * sizeof(float) +
+  size_t bytes = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + ((sizeof(TcSmem) + 15) & ~15) +
+                 (size_t)TC_M * (D.n_features + 1) * sizeof(float) +
                        (size_t)D.n_layers * ((D.n_linear - 1) * 128 + ((D.n_features + 1) / 2) * (3 * D.num_bins + 1)) *
                            sizeof(float);
+  TcArgs b = a;
+  b.act_staged = 0;
+  if (MODE == TC_TRAIN && a.act_img != nullptr && bytes + 128 + TC_EPI_WARPS * 2048 <= (size_t)227 * 1024) {
+    bytes += 128 + TC_EPI_WARPS * 2048;  // per-warp staging of the activation-image blocks
+    b.act_staged = 1;
+  }
   static size_t configured = 0;
   if (bytes > configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
@@ -600,7 +652,7 @@ static int launch_tc(const FlowmcFlowDesc& D, const TcProgram& PR, const TcArgs&
     }
     configured = bytes;
   }
-  kern<<<(unsigned)((a.n + TC_M - 1) / TC_M), TC_THREADS, bytes, stream>>>(D, PR, a);
+  kern<<<(unsigned)((a.n + TC_M - 1) / TC_M), TC_THREADS, bytes, stream>>>(D, PR, b);
   flowmc_count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
