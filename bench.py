@@ -35,6 +35,9 @@ N_LOCAL_STEPS = 1000
 STEP_SIZE = 0.1
 RHO = 0.9
 BYTES_PER_CHAIN_STEP = 4 * (D + 2)  # position (d fp32) + log-prob + accept flag, SURVEY.md 8(d)
+# from the committed ncu --set full capture of this kernel at this workload (profiles/r01_mala_c2_final_ncu.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = 7.124224e6 + 4.224889e9
+NCU_WARP_INSTR_PER_CHAIN_STEP = 534.0
 WORKLOAD = "C2: 128-D AR(1) Gaussian (rho=0.9), 8192 chains/GPU, MALA step_size=0.1, 1000 local steps per call"
 
 
@@ -171,7 +174,9 @@ def flow_extras(dev):
     ms = timed(lambda: m.train_step(x, opt.optim, opt.optim_state, idx))
     out["flow_train_c4"] = {"samples_per_s": bs / ms * 1e3, "batch": bs, "ms_per_step": ms,
                             "useful_tflops": 3 * fl * bs / ms / 1e9,
-                            "note": "forward (tcgen05) + hand-written backward (fp32 CUDA cores) + fused clip/AdamW"}
+                            "note": "training forward (tcgen05, leaves spline parameters + packed activation images) + "
+                                    "hand-written backward (tcgen05 dgrad/wgrad, in-kernel deterministic reduction) + "
+                                    "fused clip/AdamW; per-kernel split: scripts/prof_train.py"}
     # C5 global steps: 64-D, 8 layers, 65536 chains x 10 proposals
     d, n_chains, n_steps = 64, 65536, 10
     m5 = MaskedCouplingRQSpline(d, 8, [128, 128], 8, frandom.PRNGKey(1), device=dev)
@@ -381,11 +386,21 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH * (n / CHAINS_PER_GPU), "peak_source": peak_src,
+                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch "
+                                       "(profiles/r01_mala_c2_final_ncu.txt): 7.1 MB read + 4224.9 MB written = 0.993 x "
+                                       "the algorithmic bytes",
                      "kernel": "flowmc::local_steps_kernel<AR1Gaussian, MALA, Layout<...>>",
                      "algorithmic_bytes_per_launch": n * N_LOCAL_STEPS * BYTES_PER_CHAIN_STEP,
                      "avg_launch_ms": avg_kernel_ms,
-                     "note": "bit-exact threefry2x32 makes this kernel instruction-issue bound, see DESIGN.md"},
+                     "issue_slots": {
+                         "warp_instructions_per_chain_step": NCU_WARP_INSTR_PER_CHAIN_STEP,
+                         "achieved_frac": (n * N_LOCAL_STEPS / (avg_kernel_ms * 1e-3)) * NCU_WARP_INSTR_PER_CHAIN_STEP /
+                                          (148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6),
+                         "note": "executed warp-instructions (ncu smsp__inst_executed.sum / chain-steps) x measured "
+                                 "chain-steps/s over 148 SMs x 4 schedulers x the SM clock sampled during the run"},
+                     "note": "bit-exact threefry2x32 (d+5 blocks per chain-step) + XLA's erf_inv make this kernel "
+                             "instruction-issue bound, not HBM bound: see issue_slots and DESIGN.md 4.1"},
         "cpu_baseline": {"value": cpu_rate, "unit": "chain-steps/s", "cores": cpu_threads, "kind": "port",
                          "sample": f"{n} chains x {cpu_steps} MALA steps ({cpu_dt:.1f} s), same target and seeds"},
         "extra": extras,
