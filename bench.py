@@ -149,25 +149,25 @@ def flow_extras(dev):
         return 2 * L * ((d // 2) * h + h * h + h * (d // 2) * (3 * K + 1))
 
     out = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        bf16 = float(peaks["bf16_tflops"])
-    except Exception:
-        bf16 = 1590.0
-    tf32_peak = bf16 / 2.0      # dense TF32 = half the bf16 rate on this part (nominal 1.1 vs 2.25 PFLOP/s)
     # C4 flow: 32-D, 10 layers, [128,128], 8 bins
     m = MaskedCouplingRQSpline(32, 10, [128, 128], 8, frandom.PRNGKey(1), device=dev)
     n = 148 * 128 * 4
     x = frandom.normal(frandom.PRNGKey(2), (n, 32), device=dev)
     ms = timed(lambda: m.log_prob(x))
     fl = useful_flops(32, 10, 128, 8)
+    # MMAs actually issued per sample (SURVEY 8d "dense-as-written" differs: only the transformed half of W3 is
+    # multiplied, but its 4-feature chunks are padded 100 -> 112 columns and W1 sees the masked inputs as zeros)
+    issued = 10 * 2 * (32 * 128 + 128 * 128 + 4 * 128 * 112) * (3 if m.desc.tc_terms == 3 else 1)
+    pipe_peak = 4096.0 * 148 * 1.965e9 / 1e12   # kind::tf32 128x128x8 per 64 cycles per SM, at the maximum SM clock
     out["flow_log_prob_c4"] = {
         "samples_per_s": n / ms * 1e3, "useful_tflops": fl * n / ms / 1e9, "path": f"tcgen05 {m.desc.tc_terms}xTF32"
         if m.desc.tc_terms else "fp32 CUDA cores",
-        "tensor_issued_frac_of_tf32_peak": (3 if m.desc.tc_terms == 3 else 1) * 1.12 * 1.29 * fl * n / ms / 1e9 / tf32_peak,
-        "note": "issued = 3 MMA terms x 112/100 column padding x dense W1 (masked inputs are multiplied as zeros); "
-                "TF32 peak taken as bf16_tflops / 2 from MEASURED_PEAKS.json; ncu sm__pipe_tensor_cycles_active for "
-                "this kernel is in profiles/r01_flow_tc_c4_logprob_ncu.txt"}
+        "issued_tflops": issued * n / ms / 1e9,
+        "tensor_pipe_frac_from_rate": issued * n / ms / 1e9 / pipe_peak,
+        "tensor_pipe_active_ncu": 0.4706,
+        "note": "issued = 3 TF32 terms x the padded GEMM shapes; pipe peak = 4096 flop/clk/SM x 148 SMs x 1.965 GHz = "
+                "1191 TFLOP/s (the cuBLAS-measured bf16_tflops/2 = 850 understates the pipe); tensor_pipe_active_ncu = "
+                "sm__pipe_tensor_cycles_active of a 148-tile launch, profiles/r01_flow_tc_c4_logprob_v2_ncu.txt"}
     opt = Optimizer(m, 1e-3)
     bs = 16384
     idx = torch.arange(bs, dtype=torch.int32, device=dev)
