@@ -219,16 +219,44 @@ class MaskedCouplingRQSpline(NFModel):
         return dict(n_features=self._n_features, n_layers=self.n_layers, hidden_size=self.hidden_size,
                     num_bins=self.num_bins, spline_range=list(self.spline_range), n_params=int(self.desc.n_params))
 
+    def _eqx_leaves(self) -> dict:
+        from .... import eqx_io
+        n_lin = len(self.dims) - 1
+        W = [np.stack([self.weight(l, i).detach().cpu().numpy() for l in range(self.n_layers)]) for i in range(n_lin)]
+        b = [np.stack([self.bias(l, i).detach().cpu().numpy() for l in range(self.n_layers)]) for i in range(n_lin)]
+        aff = np.stack([self.affine(l).detach().cpu().numpy() for l in range(self.n_layers)])
+        return eqx_io.leaves_from_arrays(self._n_features, self.n_layers, self.hidden_size, self.num_bins,
+                                         self.spline_range, self.data_mean.cpu().numpy(), self.data_cov.cpu().numpy(),
+                                         self.base_mean.cpu().numpy(), self.base_cov.cpu().numpy(), aff[:, 0], aff[:, 1],
+                                         W, b)
+
     def save_model(self, path: str):
-        """Flat fp32 blob + JSON header (the reference's .eqx needs equinox, nf_model/base.py:92-96)."""
-        np.savez(path + ".npz", header=json.dumps(self._header()), params=self.params.detach().cpu().numpy())
+        """``path + ".eqx"`` in the reference's on-disk format (``eqx.tree_serialise_leaves``,
+        nf_model/base.py:92-93; restated in flowmc_b200/eqx_io.py), so that the file loads into a real flowMC
+        ``MaskedCouplingRQSpline`` of the same architecture and vice versa."""
+        from .... import eqx_io
+        with open(path + ".eqx", "wb") as f:
+            eqx_io.write_eqx(f, self._n_features, self.n_layers, self.hidden_size, self.num_bins, self._eqx_leaves())
 
     def load_model(self, path: str) -> "MaskedCouplingRQSpline":
-        blob = np.load(path + ".npz")
-        h = json.loads(str(blob["header"]))
-        m = MaskedCouplingRQSpline(h["n_features"], h["n_layers"], h["hidden_size"], h["num_bins"], None,
-                                   tuple(h["spline_range"]), device=self.params.device)
-        m.params.copy_(torch.from_numpy(blob["params"]))
+        """Returns a NEW model with this model's architecture and the weights of ``path + ".eqx"``
+        (nf_model/base.py:95-96: ``eqx.tree_deserialise_leaves(path + ".eqx", self)``)."""
+        from .... import eqx_io
+        with open(path + ".eqx", "rb") as f:
+            lv = eqx_io.read_eqx(f, self._n_features, self.n_layers, self.hidden_size, self.num_bins)
+        m = MaskedCouplingRQSpline(self._n_features, self.n_layers, self.hidden_size, self.num_bins, None,
+                                   self.spline_range, device=self.params.device)
+        m.tc_terms = self.tc_terms
+        dev = self.params.device
+        m.data_mean.copy_(torch.from_numpy(lv["_data_mean"]).to(dev))
+        m.data_cov.copy_(torch.from_numpy(lv["_data_cov"]).to(dev))
+        m.base_mean.copy_(torch.from_numpy(lv["base_dist._mean"]).to(dev))
+        m.base_cov.copy_(torch.from_numpy(lv["base_dist._cov"]).to(dev))
+        for l in range(self.n_layers):
+            m.affine(l).copy_(torch.tensor([lv["layers[0].bijector.scale"][l], lv["layers[0].bijector.shift"][l]]))
+            for i in range(len(self.dims) - 1):
+                m.weight(l, i).copy_(torch.from_numpy(lv[f"layers[1].bijector.conditioner.layers[{2 * i}].weight"][l]).to(dev))
+                m.bias(l, i).copy_(torch.from_numpy(lv[f"layers[1].bijector.conditioner.layers[{2 * i}].bias"][l]).to(dev))
         return m
 
     save_resource = save_model

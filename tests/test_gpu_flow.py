@@ -143,9 +143,17 @@ def test_save_load(cuda, tmp_path):
     from oracle import rng
     from flowmc_b200.resource.model.nf_model.rqSpline import MaskedCouplingRQSpline
     m = MaskedCouplingRQSpline(4, 2, [8, 8], 8, rng.PRNGKey(3))
+    m.affine(1).copy_(torch.tensor([0.3, -0.2]))
+    m.data_mean.copy_(torch.tensor([1.0, 2.0, 3.0, 4.0]))
     m.save_model(str(tmp_path / "flow"))
-    m2 = m.load_model(str(tmp_path / "flow"))
+    assert (tmp_path / "flow.eqx").exists()            # the reference's file name and format (nf_model/base.py:92-93)
+    other = MaskedCouplingRQSpline(4, 2, [8, 8], 8, rng.PRNGKey(99))   # load_model takes the architecture from self
+    m2 = other.load_model(str(tmp_path / "flow"))
     assert torch.equal(m.params, m2.params)
+    x = torch.randn(50, 4, device="cuda")
+    assert torch.equal(m.log_prob(x), m2.log_prob(x))
+    with pytest.raises(ValueError):
+        MaskedCouplingRQSpline(4, 3, [8, 8], 8, rng.PRNGKey(1)).load_model(str(tmp_path / "flow"))
 
 
 def test_tensor_core_path_is_really_used(cuda, flow_path):

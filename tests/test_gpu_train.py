@@ -227,3 +227,34 @@ def test_train_model_strategy_like_reference(cuda):
     assert torch.isfinite(res["loss"].data).all() and res["loss"].cursor == 10
     s = res["model"].sample(frandom.PRNGKey(1), 1000)
     assert torch.isfinite(s).all()
+
+
+@pytest.mark.parametrize("n", [16384, 145 * 128, 149 * 128 + 77, 3 * 148 * 128])
+def test_large_batches_tensor_core_backward(cuda, flow_path, monkeypatch, n):
+    """Batch sizes that reach every reduction path of the tensor-core backward -- 128 tiles + in-kernel reducer
+    CTAs (16384), too few spare SMs for reducers (145 tiles: stand-alone reduce kernel), more tiles than SMs
+    (persistent CTAs accumulate several tiles, ragged last tile) -- against the fp32 CUDA-core backward, which the
+    cases above pin to float64 autograd; plus bit-reproducibility (fixed-order reduction, no atomics)."""
+    if not flow_path.startswith("tcgen05"):
+        pytest.skip("compares both paths in one go")
+    p = random_params(23, 32, 3, [128, 128], 8, gain=2.0, affine=0.1)
+    r = np.random.default_rng(5)
+    x = torch.from_numpy((1.5 * r.standard_normal((n, 32))).astype(np.float32)).cuda()
+    monkeypatch.setenv("FLOWMC_FLOW_TC", "3")
+    m_tc = model_from_params(p)
+    assert m_tc.desc.tc_terms == 3 or m_tc.tc_terms == 3
+    l1, g1 = [t.clone() for t in m_tc.loss_and_grad(x)]
+    l2, g2 = [t.clone() for t in m_tc.loss_and_grad(x)]
+    assert torch.equal(g1, g2) and torch.equal(l1, l2), "tensor-core gradients are not bit-reproducible"
+    monkeypatch.setenv("FLOWMC_FLOW_TC", "0")
+    m_cc = model_from_params(p)
+    l0, g0 = [t.clone() for t in m_cc.loss_and_grad(x)]
+    assert abs(float(l1) - float(l0)) <= 1e-5 * max(1.0, abs(float(l0)))
+    a, b = _device_flat_to_oracle(m_tc, g1), _device_flat_to_oracle(m_cc, g0)
+    for name in ("W", "b"):
+        for i in range(len(a[name])):
+            tol = 2e-4 * np.abs(b[name][i]).max() + 1e-7
+            err = np.abs(a[name][i] - b[name][i]).max()
+            assert err <= tol, f"d{name}[{i}]: max err {err:.3e} > {tol:.3e}"
+    for name in ("scale", "shift"):
+        assert_close(a[name], b[name], f"d{name}", rtol=2e-4)
