@@ -174,7 +174,7 @@ class MaskedCouplingRQSpline(NFModel):
                      _stream()))
         if single:
             return y[0], ld[0]
-        return y.reshape(*lead, -1), ld.reshape(*lead)
+        return y.reshape(*lead, x2.shape[-1]), ld.reshape(*lead)   # (an empty batch cannot infer -1)
 
     def forward(self, x, key=None, condition=None):
         """Data -> latent (no whitening): returns (y, log_det) (rqSpline.py:450-468)."""
