@@ -97,6 +97,7 @@ def _load() -> C.CDLL:
         "flowmc_data_mean_cov": (i32, [vp, i64, i32, vp, vp, vp, vp]),
         "flowmc_debug_tc_timing": (None, [vp]),
         "flowmc_debug_tc_gemm": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+        "flowmc_debug_tc_gemm_pair": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
         "flowmc_nf_global_steps_workspace_bytes": (i64, [i64, i32, i32]),
         "flowmc_nf_global_steps": (i32, [C.POINTER(FlowDesc), vp, i32, vp, u32p, vp, vp, vp, vp, i64, i64, i64, i32,
                                          i32, i64, i64, C.POINTER(GlobalParams), u32p, vp, vp]),

@@ -237,6 +237,11 @@ FLOWMC_API int flowmc_data_mean_cov(const float* x, int64_t n, int d, float* mea
  * N % 16 == 0 (16..256), K % 32 == 0 (32..128); scratch: device, >= (K/32) * 2 * N * 128 bytes. */
 FLOWMC_API int flowmc_debug_tc_gemm(const float* A, const float* W, int N, int K, int terms, float* out,
                                     float* scratch, void* stream);
+/* out[256, N] = A[256, K] W[N, K]^T on a CTA pair: one 2-CTA cluster, tcgen05.mma.cta_group::2 with M = 256, each
+ * CTA holding 128 rows of A / D in its tensor memory and half of W's rows in its shared memory.  Same limits
+ * (N >= 32), same scratch. */
+FLOWMC_API int flowmc_debug_tc_gemm_pair(const float* A, const float* W, int N, int K, int terms, float* out,
+                                         float* scratch, void* stream);
 
 /* diagnostics: CTA 0 of subsequent tensor-core flow launches stamps clock64() at its pipeline events into buf
  * (device, 4 * 256 int64: weight producer / MMA issuer / epilogue thread 0 of the forward kernel, epilogue thread 0
