@@ -56,7 +56,7 @@ struct TcProgram {
 bool tc_supported(const FlowmcFlowDesc& D) {
   if (D.n_features < 2 || D.n_features > 128) return false;
   {  // shared memory: weight stages + x tile + every layer's biases must fit one CTA
-    const size_t bytes = 2048 + (size_t)4 * 32768 + (size_t)128 * (D.n_features + 1) * 4 +
+    const size_t bytes = 4096 + (size_t)4 * 32768 + (size_t)128 * (D.n_features + 1) * 4 +
                          (size_t)D.n_layers * ((D.n_linear - 1) * 128 + ((D.n_features + 1) / 2) * (3 * D.num_bins + 1)) * 4;
     if (bytes > 227 * 1024) return false;
   }
@@ -173,21 +173,27 @@ struct TcArgs {
   } while (0)
 
 struct TcSmem {
-  uint64_t stage_full[TC_STAGES], stage_empty[TC_STAGES], acc_full[2], acc_empty[2];
+  uint64_t stage_full[2 * TC_STAGES], stage_empty[2 * TC_STAGES], acc_full[2], acc_empty[2];
   uint64_t a_ready[4];  // per K-chunk (32 columns) of the A operand: a GEMM starts on the first chunk while the
                         // epilogue threads are still writing the later ones
+  uint64_t peer_full[2 * TC_STAGES];  // CTA pair, leader only: the peer CTA's half of a weight stage has landed
   uint32_t tmem_base;
   float ldpart[TC_PARTS][TC_M];
 };
 
 
-template <int KB, int MODE>
+template <int KB, int MODE, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlowDesc D, const TcProgram PR,
                                                                 const TcArgs a) {
   constexpr int NP = 3 * KB + 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* stages = smem;                                             // TC_STAGES x TC_STAGE_BYTES, 1024-aligned
+  uint8_t* stages = smem;                                             // the weight ring, 1024-aligned slots
+  // A pair streams half-size stages, so the same 128 KB hold twice as many: 8 slots = two spline chunks of
+  // prefetch.  (The ring is latency-bound, not bandwidth-bound: a slot comes back only after MMA completion ->
+  // commit -> producer -> L2 round trip, ~3.5K cycles; 4 slots give one chunk per round trip.)
+  constexpr int NST = PAIR ? 2 * TC_STAGES : TC_STAGES;
+  constexpr int SLOT = PAIR ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES;
   TcSmem* S = reinterpret_cast<TcSmem*>(smem + TC_STAGES * TC_STAGE_BYTES);
   const int d = D.n_features;
   const int xs_stride = d + 1;
@@ -204,22 +210,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
   const int L = D.n_layers, nh = D.n_linear - 1;
   const int n_pass = (MODE == TC_NF) ? 2 : 1;
   const int64_t row0 = (int64_t)blockIdx.x * TC_M;
+  // PAIR: two CTAs on neighbouring SMs (a 2-CTA cluster) run their two tiles through the same schedule as ONE
+  // M = 256 problem (tcgen05.mma.cta_group::2): each CTA keeps its own rows of A and D in its tensor memory and
+  // streams only HALF of every weight stage (N / 2 rows of the hi and lo images) into its shared memory -- the
+  // weight stream, which paces the spline-parameter GEMMs at the chip's L2 read rate, halves per SM.  The leader
+  // (cluster rank 0) issues every MMA; the peer's MMA warp only relays "my half of stage s has landed"; epilogue
+  // threads of both CTAs signal the leader's operand / accumulator barriers; MMA completions are committed to the
+  // barriers of both CTAs.
+  const uint32_t crank = PAIR ? tc::cluster_rank() : 0u;
+  constexpr uint32_t kEpiArrivals = (PAIR ? 2 : 1) * TC_EPI_WARPS;  // one arrival per epilogue warp
   if (warp == TC_EPI_WARPS + 1 && lane == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) {
+    for (int i = 0; i < NST; ++i) {
       tc::mbar_init(&S->stage_full[i], 1);
       tc::mbar_init(&S->stage_empty[i], 1);
+      tc::mbar_init(&S->peer_full[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&S->acc_full[i], 1);
-      tc::mbar_init(&S->acc_empty[i], TC_EPI);
+      tc::mbar_init(&S->acc_empty[i], kEpiArrivals);
     }
-    for (int i = 0; i < 4; ++i) tc::mbar_init(&S->a_ready[i], TC_EPI);
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&S->a_ready[i], kEpiArrivals);
     tc::fence_mbar_init();
   }
-  if (warp == TC_EPI_WARPS) tc::tmem_alloc<512>(&S->tmem_base);
+  if (warp == TC_EPI_WARPS) {
+    if (PAIR) tc::tmem_alloc_pair<512>(&S->tmem_base);
+    else tc::tmem_alloc<512>(&S->tmem_base);
+  }
   tc::tc_fence_before();
   __syncthreads();
+  if (PAIR) tc::cluster_sync();  // both CTAs' barriers and tensor memory exist before anything crosses over
   tc::tc_fence_after();
+  // epilogue -> MMA warp signal, called by whole warps (every lane has fenced its tensor-memory accesses): one
+  // arrival per warp -- in a pair the barrier lives in the leader CTA, and 256 remote arrivals per hand-off cost
+  // more than the GEMM they release
+  auto arrive_mma = [&](uint64_t* bar) {
+    __syncwarp();
+    if (lane == 0) {
+      if (!PAIR || crank == 0) tc::mbar_arrive(bar);
+      else tc::mbar_arrive_remote(bar, 0);
+    }
+  };
   const uint32_t tbase = S->tmem_base;
   const uint32_t t_ahi = tbase, t_alo = tbase + 128;
 
@@ -240,12 +270,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
               tc::mbar_wait(&S->stage_empty[s], ph ^ 1);
               if (tc::elect_one()) {
                 TC_STAMP(0);
-                tc::mbar_arrive_expect_tx(&S->stage_full[s], bytes);
-                tc::bulk_g2s(stages + (size_t)s * TC_STAGE_BYTES, lbase + it.off + (size_t)kc * bytes, bytes,
-                             &S->stage_full[s]);
+                uint8_t* dst = stages + (size_t)s * SLOT;
+                const uint8_t* src = lbase + it.off + (size_t)kc * bytes;
+                if (!PAIR) {
+                  tc::mbar_arrive_expect_tx(&S->stage_full[s], bytes);
+                  tc::bulk_g2s(dst, src, bytes, &S->stage_full[s]);
+                } else {
+                  // this CTA's rows crank * npad / 2 .. of the hi image, then of the lo image
+                  const uint32_t half = (uint32_t)it.npad * 64u;
+                  tc::mbar_arrive_expect_tx(&S->stage_full[s], 2u * half);
+                  tc::bulk_g2s(dst, src + (size_t)crank * half, half, &S->stage_full[s]);
+                  tc::bulk_g2s(dst + half, src + (size_t)it.npad * 128u + (size_t)crank * half, half, &S->stage_full[s]);
+                }
               }
               __syncwarp();
-              if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+              if (++s == NST) { s = 0; ph ^= 1; }
             }
           }
         }
@@ -253,7 +292,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // ===== MMA issuer (whole warp walks the schedule; one elected lane issues) ====================
-    {
+    if (PAIR && crank != 0) {
+      // peer CTA of a pair: no MMAs to issue; relay the arrival of this CTA's half of every weight stage
+      uint32_t s = 0, ph = 0;
+      for (int pass = 0; pass < n_pass; ++pass)
+        for (int li = 0; li < L; ++li) {
+          const int p = (((MODE == TC_INV) || (MODE == TC_NF && pass == 0)) ? L - 1 - li : li) & 1;
+          for (int ii = 0; ii < PR.n_items[p]; ++ii)
+            for (int kc = 0; kc < PR.items[p][ii].n_kc; ++kc) {
+              tc::mbar_wait(&S->stage_full[s], ph);
+              if (tc::elect_one()) tc::mbar_arrive_remote(&S->peer_full[s], 0);
+              __syncwarp();
+              if (++s == NST) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
       uint32_t s = 0, ph = 0, seq = 0, a_ph = 0;
       int n_stamp = 0;
       for (int pass = 0; pass < n_pass; ++pass) {
@@ -268,7 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
             tc::tc_fence_after();
             if (lane == 0) TC_STAMP(1);  // operands + accumulator slot available
             const uint32_t t_acc = tbase + 256 + slot * 128;
-            const uint32_t idesc = tc::make_idesc_tf32(TC_M, it.npad);
+            const uint32_t idesc = tc::make_idesc_tf32(PAIR ? 2 * TC_M : TC_M, it.npad);
             const bool three = a.terms == 3;
             for (int kc = 0; kc < it.n_kc; ++kc) {
               if (new_a) {  // K-chunk kc of the operand has been written
@@ -276,10 +329,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
                 a_ph ^= 1u << kc;
               }
               tc::mbar_wait(&S->stage_full[s], ph);
+              if (PAIR) tc::mbar_wait(&S->peer_full[s], ph);
               tc::tc_fence_after();
               if (kc == 0 && lane == 0) TC_STAMP(1);  // first weight stage landed
-              const uint32_t b_hi = tc::smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
-              const uint64_t dhi = tc::make_b_desc(b_hi), dlo = tc::make_b_desc(b_hi + it.npad * 128);
+              const uint32_t b_hi = tc::smem_u32(stages + (size_t)s * SLOT);
+              const uint64_t dhi = tc::make_b_desc(b_hi), dlo = tc::make_b_desc(b_hi + it.npad * (PAIR ? 64 : 128));
               const int ksteps = min(4, (it.K - kc * 32 + 7) >> 3);
               const uint32_t acol = kc * 32;
               if (tc::elect_one()) {
@@ -287,19 +341,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
                 for (int ks = 0; ks < 4; ++ks) {
                   if (ks < ksteps) {
                     // +32 bytes per k-step inside the 128-byte swizzle atom = +2 in the descriptor's address field
-                    tc::mma_tf32_ts(t_acc, t_ahi + acol + ks * 8, dhi + 2 * ks, idesc, (kc | ks) != 0);
-                    if (three) {
-                      tc::mma_tf32_ts(t_acc, t_alo + acol + ks * 8, dhi + 2 * ks, idesc, 1);
-                      tc::mma_tf32_ts(t_acc, t_ahi + acol + ks * 8, dlo + 2 * ks, idesc, 1);
+                    if (!PAIR) {
+                      tc::mma_tf32_ts(t_acc, t_ahi + acol + ks * 8, dhi + 2 * ks, idesc, (kc | ks) != 0);
+                      if (three) {
+                        tc::mma_tf32_ts(t_acc, t_alo + acol + ks * 8, dhi + 2 * ks, idesc, 1);
+                        tc::mma_tf32_ts(t_acc, t_ahi + acol + ks * 8, dlo + 2 * ks, idesc, 1);
+                      }
+                    } else {
+                      tc::mma_tf32_ts_pair(t_acc, t_ahi + acol + ks * 8, dhi + 2 * ks, idesc, (kc | ks) != 0);
+                      if (three) {
+                        tc::mma_tf32_ts_pair(t_acc, t_alo + acol + ks * 8, dhi + 2 * ks, idesc, 1);
+                        tc::mma_tf32_ts_pair(t_acc, t_ahi + acol + ks * 8, dlo + 2 * ks, idesc, 1);
+                      }
                     }
                   }
                 }
-                tc::mma_commit(&S->stage_empty[s]);
+                if (!PAIR) tc::mma_commit(&S->stage_empty[s]);
+                else tc::mma_commit_pair(&S->stage_empty[s], 3);
               }
               __syncwarp();
-              if (++s == TC_STAGES) { s = 0; ph ^= 1; }
+              if (++s == NST) { s = 0; ph ^= 1; }
             }
-            if (tc::elect_one()) tc::mma_commit(&S->acc_full[slot]);
+            if (tc::elect_one()) {
+              if (!PAIR) tc::mma_commit(&S->acc_full[slot]);
+              else tc::mma_commit_pair(&S->acc_full[slot], 3);
+            }
             __syncwarp();
             if (lane == 0) TC_STAMP(1);  // all MMAs of the item issued
             ++seq;
@@ -467,7 +533,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
             }
             tc::tmem_st8(t_ahi + lane_base + g * 8, hi);
             tc::tmem_st8(t_alo + lane_base + g * 8, lo);
-            if (MODE == TC_TRAIN && a.act_img != nullptr) {
+            if (MODE == TC_TRAIN && a.act_img != nullptr && row0 < a.n) {
               const int npx = tc_pad16(d);
               dump_block8(hi, lo, g * 8,
                           a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) + (size_t)q * 2 * npx * 128, npx);
@@ -476,7 +542,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
           if (hf == 0) ldacc += inv ? -(float)d * scale : (float)d * scale;
           tc::tmem_wait_st();
           tc::tc_fence_before();
-          for (int kc = 0; kc < PR.items[p][0].n_kc; ++kc) tc::mbar_arrive(&S->a_ready[kc]);
+          for (int kc = 0; kc < PR.items[p][0].n_kc; ++kc) arrive_mma(&S->a_ready[kc]);
           epi_bar();  // the row's other thread reads these x values in the spline stage
           TC_STAMP(2);  // affine + operand written
         }
@@ -509,7 +575,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
                   if (MODE == TC_TRAIN && a.save_h != nullptr && grow < a.n)
                     a.save_h[((int64_t)(l * nh + it.lin) * 128 + c + u) * a.n + grow] = hv;
                 }
-                if (MODE == TC_TRAIN && a.act_img != nullptr) {
+                if (MODE == TC_TRAIN && a.act_img != nullptr && row0 < a.n) {
                   uint8_t* gimg = a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) +
                                   tc_act_item_off(D, it.lin + 1) + (size_t)q * 2 * N * 128;
                   dump_block8(hi, lo, c, gimg, N);
@@ -522,9 +588,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
                 tc::tmem_wait_st();
               }
               tc::tc_fence_before();
-              tc::mbar_arrive(&S->a_ready[j]);
+              arrive_mma(&S->a_ready[j]);
             }
-            tc::mbar_arrive(&S->acc_empty[slot]);
+            arrive_mma(&S->acc_empty[slot]);
           } else {
             // ---- spline epilogue: this thread's half of the chunk's features ------------------------
             const int nf = it.n_feat;
@@ -575,7 +641,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
               ldacc += t0;
             }
             tc::tc_fence_before();
-            tc::mbar_arrive(&S->acc_empty[slot]);
+            arrive_mma(&S->acc_empty[slot]);
           }
           TC_STAMP(2);  // item epilogue done
           ++seq;
@@ -627,17 +693,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     tc::tc_fence_before();
   }
   __syncthreads();
+  if (PAIR) tc::cluster_sync();  // neither CTA leaves while the other may still touch its barriers / tensor memory
   tc::tc_fence_after();
-  if (warp == TC_EPI_WARPS) tc::tmem_dealloc<512>(tbase);
+  if (warp == TC_EPI_WARPS) {
+    if (PAIR) tc::tmem_dealloc_pair<512>(tbase);
+    else tc::tmem_dealloc<512>(tbase);
+  }
 }
 
-template <int KB, int MODE>
-static int launch_tc(const FlowmcFlowDesc& D, const TcProgram& PR, const TcArgs& a, cudaStream_t stream) {
-  auto kern = flow_tc_kernel<KB, MODE>;
+template <int KB, int MODE, bool PAIR>
+static int launch_tc_impl(const FlowmcFlowDesc& D, const TcProgram& PR, const TcArgs& a, cudaStream_t stream) {
+  auto kern = flow_tc_kernel<KB, MODE, PAIR>;
   size_t bytes = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + ((sizeof(TcSmem) + 15) & ~15) +
                  (size_t)TC_M * (D.n_features + 1) * sizeof(float) +
-                       (size_t)D.n_layers * ((D.n_linear - 1) * 128 + ((D.n_features + 1) / 2) * (3 * D.num_bins + 1)) *
-                           sizeof(float);
+                 (size_t)D.n_layers * ((D.n_linear - 1) * 128 + ((D.n_features + 1) / 2) * (3 * D.num_bins + 1)) *
+                     sizeof(float);
   TcArgs b = a;
   b.act_staged = 0;
   if (MODE == TC_TRAIN && a.act_img != nullptr && bytes + 128 + TC_EPI_WARPS * 2048 <= (size_t)227 * 1024) {
@@ -652,14 +722,50 @@ static int launch_tc(const FlowmcFlowDesc& D, const TcProgram& PR, const TcArgs&
     }
     configured = bytes;
   }
-  kern<<<(unsigned)((a.n + TC_M - 1) / TC_M), TC_THREADS, bytes, stream>>>(D, PR, b);
+  const unsigned tiles = (unsigned)((a.n + TC_M - 1) / TC_M);
+  cudaError_t e;
+  if (PAIR) {
+    // 2-CTA clusters: consecutive tiles pair up (an odd tile count gets one idle partner: its rows clamp to the last
+    // row and nothing of it is stored)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((tiles + 1u) & ~1u);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, D, PR, b);
+  } else {
+    kern<<<tiles, TC_THREADS, bytes, stream>>>(D, PR, b);
+    e = cudaSuccess;
+  }
   flowmc_count_launch();
-  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
     flowmc_set_error(cudaGetErrorString(e));
     return FLOWMC_ERR_CUDA;
   }
   return FLOWMC_OK;
+}
+
+// FLOWMC_TC_PAIR=1 runs the tiles as CTA pairs (cta_group::2, M = 256: each SM streams half of the weights, 8-slot
+// ring).  Verified against the oracle like the default path, but measured SLOWER on B200 (C4 log_prob 86 M vs
+// 100 M samples/s): the flow's GEMMs are short and separated by dependent epilogues, so every one of the ~15
+// hand-offs per layer now waits for the slower of two SMs plus a cross-SM signal (layer period 30.9K vs 25.3K
+// cycles, scripts/tc_timeline.py), which costs more than the halved weight stream gains.  Default: one CTA per tile.
+template <int KB, int MODE>
+static int launch_tc(const FlowmcFlowDesc& D, const TcProgram& PR, const TcArgs& a, cudaStream_t stream) {
+  static const bool pair_ok = []() {
+    const char* e = std::getenv("FLOWMC_TC_PAIR");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (pair_ok && a.n > TC_M) return launch_tc_impl<KB, MODE, true>(D, PR, a, stream);
+  return launch_tc_impl<KB, MODE, false>(D, PR, a, stream);
 }
 
 template <int MODE>

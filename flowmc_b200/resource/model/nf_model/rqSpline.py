@@ -203,6 +203,8 @@ class MaskedCouplingRQSpline(NFModel):
         key = np.ascontiguousarray(rng_key, dtype=np.uint32)
         self.prepare()
         out = torch.empty((int(n_samples), self._n_features), dtype=torch.float32, device=self.params.device)
+        if int(n_samples) == 0:
+            return out
         with torch.cuda.device(out.device):
             check(lib.flowmc_flow_sample(C.byref(self.desc), self.params.data_ptr(), None,
                                          key.ctypes.data_as(_u32p), int(n_samples), int(n_samples),
