@@ -41,8 +41,10 @@ struct GaussianMixture {
       red[m] = (m < k.K) ? expf(red[m] - mx) : 0.0f;
       s += red[m];
     }
+    // e_m / s with one correctly rounded reciprocal + a residual correction each: the same bits as eight divisions
+    const float rs = __frcp_rn(s);
 #pragma unroll
-    for (int m = 0; m < KMAX; ++m) red[m] = red[m] / s;
+    for (int m = 0; m < KMAX; ++m) red[m] = flowmc::div_const(red[m], s, rs);
     return mx + logf(s);
   }
   __device__ static float grad(const Consts& k, const flowmc::TargetCtx& c, int j, float xj, float aux,

@@ -12,11 +12,12 @@ struct Rosenbrock {
     const float u = c.x[j + 1] - xj * xj;
     const float v = 1.0f - xj;
     const bool has_next = j < c.d - 1;
-    red[0] += has_next ? (100.0f * u * u + v * v) / 20.0f : 0.0f;
-    float gj = has_next ? (400.0f * xj * u + 2.0f * v) / 20.0f : 0.0f;
+    // x / 20 as the exact 3-instruction constant division (flowmc::div_const): same bits as the division
+    red[0] += has_next ? flowmc::div_const(100.0f * u * u + v * v, 20.0f, 0.05f) : 0.0f;
+    float gj = has_next ? flowmc::div_const(400.0f * xj * u + 2.0f * v, 20.0f, 0.05f) : 0.0f;
     const float xm = c.x[j - 1];
     const float um = xj - xm * xm;
-    gj += (j > 0) ? (-200.0f * um) / 20.0f : 0.0f;
+    gj += (j > 0) ? flowmc::div_const(-200.0f * um, 20.0f, 0.05f) : 0.0f;
     return gj;
   }
   __device__ static float finish(const Consts& k, const flowmc::TargetCtx& c, float* red) { return -red[0]; }

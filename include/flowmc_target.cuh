@@ -40,6 +40,16 @@ struct TargetCtx {
   int d;
 };
 
+
+// a / b for a CONSTANT b with r = RN(1 / b) given as a literal: product + one residual correction = the IEEE
+// round-to-nearest quotient for every normal a (checked exhaustively over all float32 significands for b = 20), in 3
+// FMA-pipe instructions instead of the ~10 + slow-path branch of a true division.  Non-finite quotients pass through
+// as a * r would give them (inf / nan like a / b).
+__device__ __forceinline__ float div_const(float a, float b, float r) {
+  const float q = a * r;
+  const float c = fmaf(fmaf(-q, b, a), r, q);
+  return (fabsf(q) <= 3.402823466e+38f) ? c : q;
+}
 }  // namespace flowmc
 
 #include "../flowmc_b200/csrc/local_steps.cuh"
