@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 
 #include "flow_tc.cuh"
 #include "flow_tile.cuh"
@@ -163,7 +164,6 @@ struct TcArgs {
   float* save_theta;  // [L][ceil(d/2) * NP][n]   spline parameters (bias included) of the transformed features
   uint8_t* act_img;   // per (tile, layer): conditioner input and hidden activations as packed B stages (K = the
                       // tile's 128 rows) for the tensor-core weight-gradient GEMMs (flow_tc.cuh: tc_act_*)
-  int act_staged;     // act_img blocks go through a per-warp shared-memory buffer + bulk stores (the buffer fits)
   long long* timing;  // optional diagnostics: [3][256] clock64 stamps of CTA 0 (producer, MMA issuer, epilogue thread 0)
 };
 
@@ -192,7 +192,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
   // A pair streams half-size stages, so the same 128 KB hold twice as many: 8 slots = two spline chunks of
   // prefetch.  (The ring is latency-bound, not bandwidth-bound: a slot comes back only after MMA completion ->
   // commit -> producer -> L2 round trip, ~3.5K cycles; 4 slots give one chunk per round trip.)
-  constexpr int NST = PAIR ? 2 * TC_STAGES : TC_STAGES;
+  // Training gives the last 32 KB of the ring region to the activation-image staging buffers (4 KB per epilogue
+  // warp): the weight stream is rate-bound, not depth-bound (a 5th slot changed nothing), 3 slots keep it fed.
+  constexpr int NST = (PAIR ? 2 : 1) * (MODE == TC_TRAIN ? TC_STAGES - 1 : TC_STAGES);
   constexpr int SLOT = PAIR ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES;
   TcSmem* S = reinterpret_cast<TcSmem*>(smem + TC_STAGES * TC_STAGE_BYTES);
   const int d = D.n_features;
@@ -203,9 +205,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
   float* sbias_all = xs + TC_M * xs_stride;
   const int bias_stride = (D.n_linear - 1) * 128 + ((d + 1) / 2) * NP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // training only: per-warp staging of the activation-image blocks, [hi: 8 rows x 128 B][lo: 8 rows x 128 B]
-  uint8_t* astage_all = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(sbias_all + D.n_layers * bias_stride) + 127) & ~(uintptr_t)127);
+  uint8_t* astage_all = stages + (size_t)(TC_STAGES - 1) * TC_STAGE_BYTES;  // training only, see NST
   const float* P = a.params;
   const int L = D.n_layers, nh = D.n_linear - 1;
   const int n_pass = (MODE == TC_NF) ? 2 : 1;
@@ -386,37 +386,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     const int64_t grow = row0 + row;
     const int64_t r = min(grow, a.n - 1);
     float* xr = xs + row * xs_stride;
-    // Activation image block of 8 operand columns n0 .. n0 + 7 (= 8 image rows of 128 B: this warp's 32 samples)
-    // -> global.  Staged: the 32 lanes write their words into the warp's shared-memory buffer in image order and one
-    // lane sends the two 1 KB blocks with bulk stores (asynchronous, full lines) instead of 16 scattered 4-byte
-    // stores per thread.
-    uint8_t* astage = astage_all + warp * 2048;
-    auto dump_block8 = [&](const uint32_t* hi8, const uint32_t* lo8, int n0, uint8_t* gimg, int n_rows) {
-      if (a.act_staged) {
-        if (lane == 0) tc::bulk_wait_read<0>();  // the previous block has left the buffer
-        __syncwarp();
-        uint32_t* st = reinterpret_cast<uint32_t*>(astage);
+    // Activation image rows of NB (8 or 16) operand columns n0 .. n0 + NB - 1 (NB image rows of 128 B: this warp's
+    // 32 samples) -> global.  The 32 lanes write their words into the warp's shared-memory buffer in image order and
+    // one lane sends the hi and the lo block with two bulk stores (asynchronous, full lines, off the LSU store
+    // path, which the scattered 4-byte stores of a direct dump saturate).
+    uint8_t* astage = astage_all + warp * 4096;
+    auto dump_rows = [&](auto nb_tag, const uint32_t* hi, const uint32_t* lo, int n0, uint8_t* gimg, int n_rows) {
+      constexpr int NB = decltype(nb_tag)::value;
+      if (lane == 0) tc::bulk_wait_read<0>();  // the previous rows have left the buffer
+      __syncwarp();
+      uint32_t* st = reinterpret_cast<uint32_t*>(astage);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int o = tc::packed_b_offset(u, lane) >> 2;
-          st[o] = hi8[u];
-          st[256 + o] = lo8[u];
-        }
-        tc::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tc::bulk_s2g(gimg + (size_t)n0 * 128, astage, 1024);
-          tc::bulk_s2g(gimg + (size_t)(n_rows + n0) * 128, astage + 1024, 1024);
-          tc::bulk_commit();
-        }
-      } else {
-        uint32_t* img = reinterpret_cast<uint32_t*>(gimg);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int o = tc::packed_b_offset(n0 + u, lane) >> 2;
-          img[o] = hi8[u];
-          img[n_rows * 32 + o] = lo8[u];
-        }
+      for (int u = 0; u < NB; ++u) {
+        const int o = tc::packed_b_offset(u, lane) >> 2;
+        st[o] = hi[u];
+        st[NB * 32 + o] = lo[u];
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tc::bulk_s2g(gimg + (size_t)n0 * 128, astage, NB * 128);
+        tc::bulk_s2g(gimg + (size_t)(n_rows + n0) * 128, astage + NB * 128, NB * 128);
+        tc::bulk_commit();
       }
     };
     // this thread's share of the d features (affine / operand writes / pre / post): 8-column groups
@@ -535,8 +526,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
             tc::tmem_st8(t_alo + lane_base + g * 8, lo);
             if (MODE == TC_TRAIN && a.act_img != nullptr && row0 < a.n) {
               const int npx = tc_pad16(d);
-              dump_block8(hi, lo, g * 8,
-                          a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) + (size_t)q * 2 * npx * 128, npx);
+              dump_rows(std::integral_constant<int, 8>{}, hi, lo, g * 8,
+                        a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) + (size_t)q * 2 * npx * 128, npx);
             }
           }
           if (hf == 0) ldacc += inv ? -(float)d * scale : (float)d * scale;
@@ -578,8 +569,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
                 if (MODE == TC_TRAIN && a.act_img != nullptr && row0 < a.n) {
                   uint8_t* gimg = a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) +
                                   tc_act_item_off(D, it.lin + 1) + (size_t)q * 2 * N * 128;
-                  dump_block8(hi, lo, c, gimg, N);
-                  dump_block8(hi + 8, lo + 8, c + 8, gimg, N);
+                  dump_rows(std::integral_constant<int, 16>{}, hi, lo, c, gimg, N);
                 }
                 tc::tmem_st8(t_ahi + lane_base + c, hi);
                 tc::tmem_st8(t_ahi + lane_base + c + 8, hi + 8);
@@ -689,7 +679,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
         }
       }
     }
-    if (MODE == TC_TRAIN && a.act_staged && lane == 0) tc::bulk_wait<0>();  // this lane's bulk stores have landed
+    if (MODE == TC_TRAIN && a.act_img != nullptr && lane == 0) tc::bulk_wait<0>();  // this lane's bulk stores have landed
     tc::tc_fence_before();
   }
   __syncthreads();
@@ -709,11 +699,6 @@ static int launch_tc_impl(const FlowmcFlowDesc& D, const TcProgram& PR, const Tc
                  (size_t)D.n_layers * ((D.n_linear - 1) * 128 + ((D.n_features + 1) / 2) * (3 * D.num_bins + 1)) *
                      sizeof(float);
   TcArgs b = a;
-  b.act_staged = 0;
-  if (MODE == TC_TRAIN && a.act_img != nullptr && bytes + 128 + TC_EPI_WARPS * 2048 <= (size_t)227 * 1024) {
-    bytes += 128 + TC_EPI_WARPS * 2048;  // per-warp staging of the activation-image blocks
-    b.act_staged = 1;
-  }
   static size_t configured = 0;
   if (bytes > configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {

@@ -1,4 +1,5 @@
-"""Pipeline timeline of CTA 0 of the tensor-core flow kernel (clock64 stamps) for one log_prob launch."""
+"""Pipeline timeline of CTA 0 of the tensor-core flow kernel (clock64 stamps) for one log_prob launch
+(python scripts/tc_timeline.py [c4|c5] [terms] [train]: the training forward of one loss_and_grad call)."""
 import sys
 sys.path.insert(0, "/root/repo")
 import torch
@@ -10,11 +11,13 @@ d, L = (32, 10) if (len(sys.argv) < 2 or sys.argv[1] == "c4") else (64, 8)
 terms = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 m = MaskedCouplingRQSpline(d, L, [128, 128], 8, frandom.PRNGKey(1))
 m.tc_terms = terms
-x = frandom.normal(frandom.PRNGKey(2), (148 * 128, d))
-m.log_prob(x)
+train = len(sys.argv) > 3 and sys.argv[3] == "train"
+x = frandom.normal(frandom.PRNGKey(2), ((128 if train else 148) * 128, d))
+run = (lambda: m.loss_and_grad(x)) if train else (lambda: m.log_prob(x))
+run()
 buf = torch.zeros(4 * 256, dtype=torch.int64, device="cuda")
 lib.flowmc_debug_tc_timing(buf.data_ptr())
-m.log_prob(x)
+run()
 torch.cuda.synchronize()
 lib.flowmc_debug_tc_timing(None)
 t = buf.cpu().numpy().reshape(4, 256)[:3]
