@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
             float v[16];
             tc::tmem_ld16(tbase + 256 + lane_base + c0 + g4 * 16, v);
             tc::tmem_wait_ld();
+
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
               const float hv = __uint_as_float(hb[g4 & 1][u]) + __uint_as_float(hb[g4 & 1][16 + u]);
@@ -434,7 +435,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
     // into L2 one unit ahead
     auto prefetch_next = [&](int l, int ii) {
       int nl = l, nii = ii + 2;
-      if (nii >= PR.n_items[l & 1]) { --nl; nii = 0; }
+      if (nii >= PR.n_items[l & 1]) {
+        // last unit of layer l: finish_layer(l) will read this row's layer input (its share of the d columns)
+        const float* xin = a.save_x + ((int64_t)l * n + r) * d;
+        for (int j = j_lo; j < j_hi; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(xin + j));
+        --nl;
+        nii = 0;
+      }
       if (nl < 0) return;
       const BtItem it = PR.items[nl & 1][nii];
       if (it.kind != BK_DG3) return;
@@ -554,6 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
     // One loop, one call site per stage; the iteration after the last unit only drains: it finishes the last
     // layer and stores the last dW tile.
     int l = L - 1, ii = 0, pl = -1, pii = 0;  // current unit; previous unit (its dW tile is still in acc 1)
+    int pending_pub = -1;                     // layer whose accumulator is complete but not yet published
     while (true) {
       const bool have = l >= 0;
       if (pl >= 0 && (!have || l != pl)) finish_layer(pl);  // [F] layer boundary: needs the dgrad of the last unit
@@ -567,11 +575,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
         prefetch_next(l, ii);
       }
       if (pl >= 0) reduce_unit(pl, pii);                    // [C] overlaps the dgrad MMAs
-      if (last && a.done != nullptr && pl >= 0 && (!have || l != pl)) {
-        // layer pl of this CTA's accumulator is final: publish it to the reducer CTAs
-        __threadfence();
-        epi_bar();
-        if (tid == 0) atomicAdd(a.done + pl, 1);
+      if (last && a.done != nullptr) {
+        // Layer pl of this CTA's accumulator is final after the store above: publish it to the reducer CTAs -- one
+        // unit LATER (its stores have drained by then, so the fence is cheap), at once when nothing follows.
+        if (pending_pub >= 0) {
+          __threadfence();
+          epi_bar();
+          if (tid == 0) atomicAdd(a.done + pending_pub, 1);
+          pending_pub = -1;
+        }
+        if (pl >= 0 && (!have || l != pl)) {
+          if (have) {
+            pending_pub = pl;
+          } else {
+            __threadfence();
+            epi_bar();
+            if (tid == 0) atomicAdd(a.done + pl, 1);
+          }
+        }
       }
       BT_STAMP();
       if (!have) break;

@@ -19,7 +19,7 @@ t = buf.cpu().numpy().reshape(4, 256)[3]
 v = t[t > 0]
 v = v - v[0]
 print("backward epilogue stamps per chunk: [operand written, dgrad done, transposed written, wgrad done, reduced]")
-print(" ".join(str(int(c)) for c in v[:60]))
+print(" ".join(str(int(c)) for c in v[:120]))
 import numpy as np
-dv = np.diff(v[:41])
+dv = np.diff(v[:100])
 print("deltas:", " ".join(str(int(c)) for c in dv))
