@@ -77,6 +77,8 @@ def _load() -> C.CDLL:
         "flowmc_random_normal": (i32, [u32p, i64, vp, vp]),
         "flowmc_local_steps": (i32, [i32, i32, vp, u32p, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i64, i64,
                                      C.POINTER(LocalParams), u32p, vp, vp]),
+        "flowmc_adam_optimize": (i32, [i32, vp, u32p, vp, i64, i32, i32, f32, f32, vp, vp, vp, i64, i64, u32p, vp, vp,
+                                       vp]),
         "flowmc_launch_count": (i64, []),
         "flowmc_local_steps_workspace_bytes": (i64, [i64, i32, i32]),
         "flowmc_flow_desc_init": (i32, [C.POINTER(FlowDesc), i32, i32, i32, C.POINTER(C.c_int), i32, f32, f32]),

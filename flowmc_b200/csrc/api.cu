@@ -222,4 +222,50 @@ int flowmc_local_steps(int kind, int target_id, const float* target_data, const 
   return vt.local_steps(kind, &a, (cudaStream_t)stream);
 }
 
+int flowmc_adam_optimize(int target_id, const float* target_data, const uint32_t key[2], const float* x0,
+                         int64_t n_chains, int d, int n_steps, float learning_rate, float noise_level,
+                         const float* bounds_lo, const float* bounds_hi, const float* bias_corrections,
+                         int64_t chain_offset, int64_t n_chains_global, uint32_t key_out[2], float* x_out,
+                         float* logp_out, void* stream) {
+  FlowmcTargetVTable vt;
+  if (int rc = flowmc_get_target(target_id, &vt)) return rc;
+  if (!key || !key_out) return fail(FLOWMC_ERR_INVALID, "adam_optimize: null key");
+  if (n_chains < 0 || d <= 0 || n_steps < 0) return fail(FLOWMC_ERR_INVALID, "adam_optimize: bad sizes");
+  if (chain_offset < 0 || chain_offset + n_chains > n_chains_global)
+    return fail(FLOWMC_ERR_INVALID, "adam_optimize: chain shard outside [0, n_chains_global)");
+  if (!vt.adam_opt) return fail(FLOWMC_ERR_UNSUPPORTED, "adam_optimize: target plugin built against an older header");
+  // optimization.py:149: rng_key, subkey = split(rng_key)
+  const flowmc::Key k{key[0], key[1]};
+  const flowmc::Key knew = flowmc::split_at(k, 0);
+  const flowmc::Key sub = flowmc::split_at(k, 1);
+  key_out[0] = knew.k0;
+  key_out[1] = knew.k1;
+  if (n_chains == 0) return FLOWMC_OK;
+  if (!x0 || !x_out || !bounds_lo || !bounds_hi || (n_steps > 0 && !bias_corrections))
+    return fail(FLOWMC_ERR_INVALID, "adam_optimize: null buffer");
+  flowmc::AdamOptArgs a;
+  a.data = target_data;
+  a.x0 = x0;
+  a.x_out = x_out;
+  a.lp_out = logp_out;
+  a.n_chains = n_chains;
+  a.chain_offset = chain_offset;
+  a.d = d;
+  a.n_steps = n_steps;
+  a.subkey = sub;
+  // optax.adam defaults (optimization.py:61-63): b1 = 0.9, b2 = 0.999, eps = 1e-8; Python-float hyper-parameters
+  // meet float32 arrays as float32 scalars
+  a.neg_lr = -learning_rate;
+  a.noise_level = noise_level;
+  a.eps = 1e-8f;
+  a.b1 = 0.9f;
+  a.b2 = 0.999f;
+  a.one_minus_b1 = (float)(1.0 - 0.9);
+  a.one_minus_b2 = (float)(1.0 - 0.999);
+  a.bc = bias_corrections;
+  a.lo = bounds_lo;
+  a.hi = bounds_hi;
+  return vt.adam_opt(&a, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -4,7 +4,7 @@
 #include <cuda_runtime.h>
 #include "rng.cuh"
 
-#define FLOWMC_TARGET_ABI 1
+#define FLOWMC_TARGET_ABI 2
 
 namespace flowmc {
 
@@ -36,6 +36,24 @@ struct LocalArgs {
   int64_t workspace_bytes;
 };
 
+// arguments of the AdamOptimization kernel (adam_opt.cuh)
+struct AdamOptArgs {
+  const float* data;      // packed target parameters
+  const float* x0;        // [n_chains, d]
+  float* x_out;           // [n_chains, d]
+  float* lp_out;          // [n_chains] logpdf(x_out), optional
+  int64_t n_chains;
+  int64_t chain_offset;   // global index of local chain 0
+  int d;
+  int n_steps;
+  Key subkey;             // chain c uses split(subkey, n_chains_global)[chain_offset + c]
+  float neg_lr, noise_level, eps, b1, b2, one_minus_b1, one_minus_b2;
+  const float* bc;        // device [n_steps, 2]
+  const float* lo;        // device [d] lower bounds (-inf allowed)
+  const float* hi;        // device [d]
+};
+
+
 }  // namespace flowmc
 
 extern "C" {
@@ -46,6 +64,7 @@ typedef struct FlowmcTargetVTable {
   int (*local_steps)(int kind, const flowmc::LocalArgs* args, cudaStream_t stream);
   int (*eval)(const float* data, const float* x, int64_t n, int d, float* logp_out, float* grad_out,
               cudaStream_t stream);
+  int (*adam_opt)(const flowmc::AdamOptArgs* args, cudaStream_t stream);  // AdamOptimization (ABI >= 2)
 } FlowmcTargetVTable;
 
 __attribute__((visibility("default"))) int flowmc_register_target(const FlowmcTargetVTable* vt);

@@ -231,6 +231,19 @@ FLOWMC_API int flowmc_gather_training_rows(const float* buf, const int32_t* rowm
 FLOWMC_API int flowmc_data_mean_cov(const float* x, int64_t n, int d, float* mean, float* cov, float* scratch,
                                     void* stream);
 
+/* ---- AdamOptimization (src/flowMC/strategy/optimization.py:85-164) ---------------------------------------- */
+/* n_steps of optax.adam(learning_rate) on -logpdf for every chain, gradient multiplied by (1 + normal * noise_level),
+ * box projection after every step; one launch, chain state in registers.  key: the strategy's rng_key (host);
+ * key_out: the key the strategy returns.  x0 / x_out: device [n_chains, d]; bounds_lo / bounds_hi: device [d];
+ * bias_corrections: device [n_steps, 2] float32 = {1 - 0.9^(t+1), 1 - 0.999^(t+1)}; logp_out: device [n_chains] or
+ * NULL.  chain_offset / n_chains_global: this process's shard of the global chain index space (keys come from the
+ * global split, so any sharding gives the same result). */
+FLOWMC_API int flowmc_adam_optimize(int target_id, const float* target_data, const uint32_t key[2], const float* x0,
+                                    int64_t n_chains, int d, int n_steps, float learning_rate, float noise_level,
+                                    const float* bounds_lo, const float* bounds_hi, const float* bias_corrections,
+                                    int64_t chain_offset, int64_t n_chains_global, uint32_t key_out[2], float* x_out,
+                                    float* logp_out, void* stream);
+
 /* ---- diagnostics ---------------------------------------------------------------------------------------- */
 /* out[128, N] = A[128, K] W[N, K]^T through the tcgen05 path (A in TMEM, W as packed swizzled stages, kind::tf32,
  * terms = 1: plain TF32, 3: 3xTF32).  Unit-test hook for the operand conventions of the tensor-core flow kernels.

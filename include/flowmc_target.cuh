@@ -53,6 +53,7 @@ __device__ __forceinline__ float div_const(float a, float b, float r) {
 }  // namespace flowmc
 
 #include "../flowmc_b200/csrc/local_steps.cuh"
+#include "../flowmc_b200/csrc/adam_opt.cuh"
 #include "../flowmc_b200/csrc/registry.h"
 
 // Registers target struct T under `NAME` at load time (static initialiser).
@@ -65,6 +66,7 @@ __device__ __forceinline__ float div_const(float a, float b, float r) {
       vt.name = NAME;                                                                           \
       vt.local_steps = &flowmc::launch_local_steps<T>;                                          \
       vt.eval = &flowmc::launch_target_eval<T>;                                                 \
+      vt.adam_opt = &flowmc::launch_adam_opt<T>;                                                \
       flowmc_register_target(&vt);                                                              \
     }                                                                                           \
   };                                                                                            \

@@ -161,3 +161,22 @@ def test_select_training_data_layout():
     key, tkey, data, idx = nf.select_training_data(rng.PRNGKey(0), buf, 50, 3)
     pop = buf[:, 3:6].reshape(-1, d)
     assert np.array_equal(data, pop[idx]) and idx.max() < 12 and data.shape == (50, d)
+
+
+def test_adam_optimization_restatement_meets_the_reference_invariants():
+    """test/unit/test_strategies.py:40-78 on the oracle's AdamOptimization (oracle/optimization.py)."""
+    from oracle import optimization as oopt, rng, targets as O
+    key = rng.PRNGKey(42)
+    key, sub = rng.split(key)
+    x0 = (rng.normal(sub, (20, 2)) * 1 + 10).astype(np.float32)
+    data = O.IsoGaussian.pack(2, 0.5, np.arange(2))
+    new_key, x, lp = oopt.adam_optimize(key, "iso_gaussian", data, x0, n_steps=100, learning_rate=5e-2, noise_level=0.0)
+    assert x.shape == (20, 2) and lp.shape == (20,)
+    assert np.all(x.mean(axis=1) < x0.mean(axis=1)) and np.all(np.isfinite(lp))
+    assert np.array_equal(new_key, rng.split(key)[0])
+    # Adam moves every coordinate by at most ~lr per step towards the optimum: 100 steps of 0.05
+    assert np.all((x0 - x) > 3.5) and np.all((x0 - x) < 5.01)
+    # the box projection holds at every step, noise or not; same key -> same result
+    _, xb, _ = oopt.adam_optimize(key, "iso_gaussian", data, x0, n_steps=30, noise_level=10.0, bounds=[[9.0, 10.5]])
+    _, xb2, _ = oopt.adam_optimize(key, "iso_gaussian", data, x0, n_steps=30, noise_level=10.0, bounds=[[9.0, 10.5]])
+    assert xb.min() >= 9.0 and xb.max() <= 10.5 and np.array_equal(xb, xb2)
