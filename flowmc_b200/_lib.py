@@ -27,6 +27,9 @@ class LocalParams(C.Structure):
         ("lp0", C.c_void_p),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_int64),
+        ("chain_keys", C.c_void_p),
+        ("beta", C.c_void_p),
+        ("prior", C.c_void_p),
     ]
 
 
@@ -79,6 +82,7 @@ def _load() -> C.CDLL:
                                      C.POINTER(LocalParams), u32p, vp, vp]),
         "flowmc_adam_optimize": (i32, [i32, vp, u32p, vp, i64, i32, i32, f32, f32, vp, vp, vp, i64, i64, u32p, vp, vp,
                                        vp]),
+        "flowmc_pt_exchange": (i32, [u32p, i64, i64, i64, i32, i32, vp, vp, vp, vp, vp]),
         "flowmc_launch_count": (i64, []),
         "flowmc_local_steps_workspace_bytes": (i64, [i64, i32, i32]),
         "flowmc_flow_desc_init": (i32, [C.POINTER(FlowDesc), i32, i32, i32, C.POINTER(C.c_int), i32, f32, f32]),

@@ -55,6 +55,39 @@ __global__ void random_normal_kernel(flowmc::Key key, int64_t n, float* __restri
     out[i] = flowmc::bits_to_normal(flowmc::bits_at(key, (uint64_t)i));
 }
 
+// ParallelTempering._exchange (strategy/parallel_tempering.py:291-398): one thread per chain walks the
+// temperature ladder, idx = 0 .. n_temps - 2: key, sub = split(key); accept the swap of rungs idx / idx + 1 when
+// log(uniform(sub)) < (1 / T[idx+1] - 1 / T[idx]) * (lp[idx] - lp[idx+1]), lp = the UNtempered log-density, which is
+// swapped along with the position.
+__global__ void pt_exchange_kernel(flowmc::Key subkey, int64_t chain_offset, int64_t n_chains, int n_temps, int d,
+                                   float* __restrict__ pos, float* __restrict__ lp, const float* __restrict__ temps,
+                                   float* __restrict__ acc) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chains) return;
+  flowmc::Key key = flowmc::split_at(subkey, (uint64_t)(chain_offset + c));
+  float* P = pos + c * n_temps * d;
+  float* Lp = lp + c * n_temps;
+  for (int idx = 0; idx + 1 < n_temps; ++idx) {
+    const flowmc::Key sub = flowmc::split_at(key, 1);
+    key = flowmc::split_at(key, 0);
+    const float ratio = __fmul_rn(__fsub_rn(__fdiv_rn(1.0f, temps[idx + 1]), __fdiv_rn(1.0f, temps[idx])),
+                                  __fsub_rn(Lp[idx], Lp[idx + 1]));
+    const float log_uniform = logf(flowmc::bits_to_uniform01(flowmc::bits_at(sub, 0)));
+    const bool accept = log_uniform < ratio;
+    if (accept) {
+      for (int j = 0; j < d; ++j) {
+        const float t = P[idx * d + j];
+        P[idx * d + j] = P[(idx + 1) * d + j];
+        P[(idx + 1) * d + j] = t;
+      }
+      const float t = Lp[idx];
+      Lp[idx] = Lp[idx + 1];
+      Lp[idx + 1] = t;
+    }
+    acc[c * (n_temps - 1) + idx] = accept ? 1.0f : 0.0f;
+  }
+}
+
 inline unsigned grid_for(int64_t n, int block) {
   int64_t g = (n + block - 1) / block;
   const int64_t cap = 148 * 16;  // a few waves over the 148 SMs; kernels are grid-stride
@@ -159,6 +192,21 @@ int flowmc_random_normal(const uint32_t key[2], int64_t n, float* out, void* str
   return check_launch("random_normal");
 }
 
+int flowmc_pt_exchange(const uint32_t subkey[2], int64_t chain_offset, int64_t n_chains_global, int64_t n_chains,
+                       int n_temps, int d, float* positions, float* log_probs, const float* temperatures,
+                       float* accepts, void* stream) {
+  if (!subkey || n_chains < 0 || n_temps < 1 || d <= 0)
+    return fail(FLOWMC_ERR_INVALID, "pt_exchange: bad arguments");
+  if (chain_offset < 0 || chain_offset + n_chains > n_chains_global)
+    return fail(FLOWMC_ERR_INVALID, "pt_exchange: chain shard outside [0, n_chains_global)");
+  if (n_chains == 0 || n_temps == 1) return FLOWMC_OK;
+  if (!positions || !log_probs || !temperatures || !accepts) return fail(FLOWMC_ERR_INVALID, "pt_exchange: null buffer");
+  pt_exchange_kernel<<<(unsigned)((n_chains + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      flowmc::Key{subkey[0], subkey[1]}, chain_offset, n_chains, n_temps, d, positions, log_probs, temperatures, accepts);
+  flowmc_count_launch();
+  return check_launch("pt_exchange");
+}
+
 int64_t flowmc_local_steps_workspace_bytes(int64_t n_chains, int d, int layout_hint) {
   if (n_chains <= 0 || d <= 0) return 0;
   return flowmc::local_workspace_bytes(n_chains, d, layout_hint);
@@ -219,6 +267,9 @@ int flowmc_local_steps(int kind, int target_id, const float* target_data, const 
   a.lp0 = params->lp0;
   a.workspace = params->workspace;
   a.workspace_bytes = params->workspace_bytes;
+  a.chain_keys = params->chain_keys;
+  a.beta = params->beta;
+  a.prior = params->prior;
   return vt.local_steps(kind, &a, (cudaStream_t)stream);
 }
 

@@ -40,7 +40,9 @@
 
 namespace flowmc {
 
-enum : int { KIND_MALA = 0, KIND_HMC = 1, KIND_GRW = 2 };
+// KIND_MALA_PT: MALA on the TEMPERED density beta_c * logpdf(x) + log_prior(x) with a per-chain inverse temperature
+// (ParallelTempering's individual steps, strategy/parallel_tempering.py:189-197; resource/logPDF.py:104-106)
+enum : int { KIND_MALA = 0, KIND_HMC = 1, KIND_GRW = 2, KIND_MALA_PT = 3 };
 
 constexpr int kChunk = 32;  // steps per key-schedule chunk (= one step per lane)
 
@@ -121,6 +123,38 @@ __device__ __forceinline__ float eval_target(const typename T::Consts& tc, const
     }
   }
   __syncwarp();  // xrow/scratch may be overwritten by the next evaluation
+  return lp;
+}
+
+// Tempered evaluation: beta * logpdf(x) + log_prior(x) and its gradient.  The prior is the fixed-function family
+// log_prior(x) = -sum_j c_j (x_j - m_j)^2 inside the box [lo, hi], -inf outside (Gaussian, uniform and flat priors);
+// prior == nullptr is the flat prior 0 (test/unit/test_strategies.py:345-350).  prior layout: [4][d] = c, m, lo, hi.
+template <class T, class L, bool WANT_GRAD>
+__device__ __forceinline__ float eval_tempered(const typename T::Consts& tc, const float (&xv)[L::kDPL],
+                                               float (&gv)[L::kDPL], float* xrow, float* scratch, const float* data,
+                                               int d, int lg, float beta, const float* prior) {
+  constexpr int DPL = L::kDPL, G = L::kG;
+  float lp = beta * eval_target<T, L, WANT_GRAD>(tc, xv, gv, xrow, scratch, data, d, lg);
+  if (WANT_GRAD) {
+#pragma unroll
+    for (int k = 0; k < DPL; ++k) gv[k] = beta * gv[k];
+  }
+  if (prior != nullptr) {
+    float ps = 0.0f, outside = 0.0f;
+#pragma unroll
+    for (int k = 0; k < DPL; ++k) {
+      const int j = L::dim(k, lg);
+      if (L::valid(j, d)) {
+        const float c = __ldg(prior + j), r = xv[k] - __ldg(prior + d + j);
+        ps += c * r * r;
+        if (xv[k] < __ldg(prior + 2 * d + j) || xv[k] > __ldg(prior + 3 * d + j)) outside = 1.0f;
+        if (WANT_GRAD) gv[k] += -2.0f * c * r;
+      }
+    }
+    ps = group_sum<G>(ps);
+    outside = group_sum<G>(outside);
+    lp += (outside > 0.0f) ? -INFINITY : -ps;
+  }
   return lp;
 }
 
@@ -224,12 +258,22 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
   }
   __syncwarp();
   const typename T::Consts tc = T::prepare(a.data, d);
+  constexpr bool IS_MALA = KIND == KIND_MALA || KIND == KIND_MALA_PT;
+  constexpr bool TEMPERED = KIND == KIND_MALA_PT;
+  const float beta = (TEMPERED && a.beta != nullptr) ? a.beta[chain] : 1.0f;
+  // one evaluation of the (tempered) target at a point
+  auto eval_grad = [&](const float (&xv)[DPL], float (&gv)[DPL]) -> float {
+    if (TEMPERED) return eval_tempered<T, L, true>(tc, xv, gv, xrow, scratch, a.data, d, lg, beta, a.prior);
+    return eval_target<T, L, true>(tc, xv, gv, xrow, scratch, a.data, d, lg);
+  };
 
   Key kc;
   float x[DPL], g[DPL], lp;
   if (seg == 0) {
     // per-chain key: split(subkey, n_chains_global)[global chain index]   (take_steps.py:72)
     kc = split_at(a.subkey, (uint64_t)(a.chain_offset + chain));
+    // ... or an explicit per-chain key (ParallelTempering: split(split(subkey, n_chains)[c], n_temps)[t])
+    if (a.chain_keys != nullptr) kc = Key{a.chain_keys[2 * chain], a.chain_keys[2 * chain + 1]};
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
       const int j = L::dim(k, lg);
@@ -237,7 +281,8 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
       g[k] = 0.0f;
     }
     // logpdf(initial_position) seeds the scan carry (take_steps.py:177); MALA/HMC cache the gradient
-    lp = eval_target<T, L, KIND != KIND_GRW>(tc, x, g, xrow, scratch, a.data, d, lg);
+    if (TEMPERED) lp = eval_grad(x, g);
+    else lp = eval_target<T, L, KIND != KIND_GRW>(tc, x, g, xrow, scratch, a.data, d, lg);
     if (a.lp0 != nullptr) lp = a.lp0[chain];  // ProposalBase.kernel(): caller-supplied log_prob
   } else {
     // wait for the previous time slice of this group, then pick up its state
@@ -323,7 +368,7 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
       const float logu = sm.logu[cw][tt];
       bool acc;
 
-      if (KIND == KIND_MALA) {
+      if (IS_MALA) {
         float prop[DPL], g1[DPL];
         draw_normals<L>(key1, d, lg, prop);  // prop holds z for now
         float qa = 0.0f;
@@ -334,7 +379,7 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
           const float y = prop[k] - mean;
           qa += y * y;
         }
-        const float lp1 = eval_target<T, L, true>(tc, prop, g1, xrow, scratch, a.data, d, lg);
+        const float lp1 = eval_grad(prop, g1);
         float qb = 0.0f;
 #pragma unroll
         for (int k = 0; k < DPL; ++k) {
@@ -656,6 +701,7 @@ int launch_local_steps(int kind, const LocalArgs* a, cudaStream_t stream) {
     case KIND_MALA: return launch_local_kind<T, KIND_MALA>(a, stream);
     case KIND_HMC: return launch_local_kind<T, KIND_HMC>(a, stream);
     case KIND_GRW: return launch_local_kind<T, KIND_GRW>(a, stream);
+    case KIND_MALA_PT: return launch_local_kind<T, KIND_MALA_PT>(a, stream);
     default:
       flowmc_set_error("local_steps: unknown kernel kind");
       return -1;

@@ -32,6 +32,9 @@ struct LocalArgs {
   int layout_hint;
   const uint32_t* step_keys;  // optional [n_chains,2]; n_steps must be 1
   const float* lp0;           // optional [n_chains]
+  const uint32_t* chain_keys; // optional [n_chains,2]: initial per-chain keys instead of split(subkey)[c]
+  const float* beta;          // KIND_MALA_PT: [n_chains] inverse temperatures (NULL = 1)
+  const float* prior;         // KIND_MALA_PT: [4][d] = c, m, lo, hi of the quadratic / box log-prior (NULL = 0)
   void* workspace;            // optional: time-slicing scratch (see local_steps.cuh)
   int64_t workspace_bytes;
 };

@@ -48,6 +48,7 @@ extern "C" {
 #define FLOWMC_KERNEL_MALA 0
 #define FLOWMC_KERNEL_HMC 1
 #define FLOWMC_KERNEL_GRW 2
+#define FLOWMC_KERNEL_MALA_TEMPERED 3 /* MALA on beta_c * logpdf + log_prior (ParallelTempering) */
 
 /* error codes */
 #define FLOWMC_OK 0
@@ -95,6 +96,12 @@ typedef struct FlowmcLocalParams {
                            * CTAs when there are more chain groups than resident slots); size from
                            * flowmc_local_steps_workspace_bytes().  NULL = plain one-CTA-per-group grid */
   int64_t workspace_bytes;
+  const uint32_t* chain_keys; /* optional, device [n_chains,2]: the chains' initial keys; NULL = split(subkey,
+                               * n_chains_global)[global chain index] (take_steps.py:72).  ParallelTempering passes
+                               * split(split(subkey, n_chains)[c], n_temps)[t] (parallel_tempering.py:289-293) */
+  const float* beta;      /* FLOWMC_KERNEL_MALA_TEMPERED: device [n_chains] inverse temperatures 1 / T (NULL = 1) */
+  const float* prior;     /* FLOWMC_KERNEL_MALA_TEMPERED: device [4, d] = c, m, lo, hi of
+                           * log_prior(x) = -sum_j c_j (x_j - m_j)^2 inside [lo, hi], -inf outside; NULL = flat 0 */
 } FlowmcLocalParams;
 
 /* bytes of `workspace` that flowmc_local_steps can use for (n_chains, d, layout_hint) */
@@ -230,6 +237,17 @@ FLOWMC_API int flowmc_gather_training_rows(const float* buf, const int32_t* rowm
 /* jnp.mean(x, 0) and jnp.cov(x.T) of x device [n, d]; scratch: device, >= d floats */
 FLOWMC_API int flowmc_data_mean_cov(const float* x, int64_t n, int d, float* mean, float* cov, float* scratch,
                                     void* stream);
+
+/* ---- ParallelTempering exchange step (src/flowMC/strategy/parallel_tempering.py:291-398) ----------------- */
+/* For every chain, in ladder order idx = 0 .. n_temps - 2: key, sub = split(key) (key = split(subkey,
+ * n_chains_global)[global chain]); swap rungs idx and idx + 1 (positions AND log_probs) when
+ * log(uniform(sub)) < (1 / T[idx+1] - 1 / T[idx]) * (log_probs[idx] - log_probs[idx+1]).  In place.
+ * positions: device [n_chains, n_temps, d]; log_probs: device [n_chains, n_temps] UNtempered logpdf(positions);
+ * temperatures: device [n_temps]; accepts: device [n_chains, n_temps - 1] (0 / 1).  The tempered individual steps
+ * that precede it are flowmc_local_steps(FLOWMC_KERNEL_MALA_TEMPERED) with chain_keys / beta / prior. */
+FLOWMC_API int flowmc_pt_exchange(const uint32_t subkey[2], int64_t chain_offset, int64_t n_chains_global,
+                                  int64_t n_chains, int n_temps, int d, float* positions, float* log_probs,
+                                  const float* temperatures, float* accepts, void* stream);
 
 /* ---- AdamOptimization (src/flowMC/strategy/optimization.py:85-164) ---------------------------------------- */
 /* n_steps of optax.adam(learning_rate) on -logpdf for every chain, gradient multiplied by (1 + normal * noise_level),

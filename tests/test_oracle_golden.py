@@ -180,3 +180,30 @@ def test_adam_optimization_restatement_meets_the_reference_invariants():
     _, xb, _ = oopt.adam_optimize(key, "iso_gaussian", data, x0, n_steps=30, noise_level=10.0, bounds=[[9.0, 10.5]])
     _, xb2, _ = oopt.adam_optimize(key, "iso_gaussian", data, x0, n_steps=30, noise_level=10.0, bounds=[[9.0, 10.5]])
     assert xb.min() >= 9.0 and xb.max() <= 10.5 and np.array_equal(xb, xb2)
+
+
+def test_parallel_tempering_restatement_invariants():
+    """oracle/parallel_tempering.py: shapes and invariants of test/unit/test_strategies.py:337-520."""
+    from oracle import parallel_tempering as opt, rng, targets as O
+    key = rng.PRNGKey(42)
+    key, sub = rng.split(key)
+    x0 = rng.normal(sub, (7, 3))
+    key, sub = rng.split(key)
+    tp = rng.normal(sub, (7, 4, 3))
+    temps = (np.arange(5) + 1.0).astype(np.float32)
+    data = O.IsoGaussian.pack(3, 0.5, np.arange(3))
+    k1, p0, tpos, t2, accs = opt.parallel_tempering(key, x0, tp, temps, "iso_gaussian", data, 4, 1.0)
+    k2, p0b, _, _, _ = opt.parallel_tempering(key, x0, tp, temps, "iso_gaussian", data, 4, 1.0)
+    assert p0.shape == (7, 3) and tpos.shape == (7, 4, 3) and accs.shape == (7, 4)
+    assert np.array_equal(p0, p0b) and np.array_equal(k1, k2)                 # deterministic in the key
+    assert t2[0] == temps[0] and t2[-1] == temps[-1]                          # the ladder's ends never move
+    # equal acceptance on every rung leaves the ladder unchanged (test_adapt_temperatures)
+    t = (np.arange(5) * 0.3 + 1).astype(np.float32)
+    assert np.allclose(opt.adapt_temperature(t, np.ones((7, 4), np.float32)), t)
+    # an exchange only permutes the rungs of a chain
+    pos = np.concatenate([x0[:, None, :], tp], axis=1)
+    out, lp, acc, _, _ = opt.exchange(sub, pos, "iso_gaussian", data, t)
+    assert np.allclose(np.sort(out.sum(axis=2), axis=1), np.sort(pos.sum(axis=2), axis=1))
+    # not training: buffers untouched
+    _, _, tpos_nt, t_nt, _ = opt.parallel_tempering(key, x0, tp, temps, "iso_gaussian", data, 4, 1.0, training=False)
+    assert np.array_equal(tpos_nt, tp) and np.array_equal(t_nt, temps)
