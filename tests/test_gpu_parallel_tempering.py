@@ -158,3 +158,33 @@ class TestTemperingStrategies:
         resources["MALA"] = GaussianRandomWalk(0.1)
         with pytest.raises(NotImplementedError):
             strat(key, resources, x0, self._data())
+
+
+def test_rqspline_mala_pt_bundle(cuda):
+    """test/unit/test_bundle.py:35-58 (construction, repr) + a short end-to-end Sampler run through the bundle."""
+    from flowmc_b200 import random as frandom, targets as T
+    from flowmc_b200.Sampler import Sampler
+    from flowmc_b200.resource.logPDF import BoxQuadraticPrior
+    from flowmc_b200.resource_strategy_bundle.RQSpline_MALA_PT import RQSpline_MALA_PT_Bundle
+    n_chains, n_dims = 16, 3
+    rng_key = frandom.PRNGKey(0)
+    bundle = RQSpline_MALA_PT_Bundle(rng_key=rng_key, n_chains=n_chains, n_dims=n_dims, logpdf=T.iso_gaussian(0.5, "data"),
+                                     n_local_steps=10, n_global_steps=5, n_training_loops=2, n_production_loops=1,
+                                     n_epochs=3, batch_size=64, n_max_examples=200,
+                                     logprior=BoxQuadraticPrior(c=0.01, lower=-20.0, upper=20.0))
+    assert repr(bundle) == "RQSpline MALA PT Bundle"
+    assert bundle.strategy_order[0] == "initialize_tempered_positions"
+    assert bundle.strategy_order.count("parallel_tempering") == 3
+    assert bundle.resources["tempered_positions"].shape == (n_chains, 4, n_dims)
+    assert torch.allclose(bundle.resources["temperatures"].data.cpu(), torch.linspace(1.0, 5.0, 5))
+    key, sub = frandom.split(frandom.PRNGKey(1))
+    sampler = Sampler(n_dims, n_chains, key, resource_strategy_bundles=bundle)
+    x0 = frandom.normal(sub, (n_chains, n_dims))
+    sampler.sample(x0, {"data": np.arange(n_dims, dtype=np.float32)})
+    prod = sampler.resources["positions_production"].data
+    assert prod.shape == (n_chains, 15, n_dims) and bool(torch.isfinite(prod).all())
+    tp = sampler.resources["tempered_positions"].data
+    assert bool(torch.isfinite(tp).all()) and not torch.equal(tp[:, 0], tp[:, 1])
+    t = sampler.resources["temperatures"].data
+    assert float(t[0]) == 1.0 and float(t[-1]) == 5.0 and bool(torch.isfinite(t).all())
+    assert sampler.resources["sampler_state"].data["training"] is False
