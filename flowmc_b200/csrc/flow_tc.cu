@@ -209,7 +209,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
   const float* P = a.params;
   const int L = D.n_layers, nh = D.n_linear - 1;
   const int n_pass = (MODE == TC_NF) ? 2 : 1;
-  const int64_t row0 = (int64_t)blockIdx.x * TC_M;
+  // persistent CTAs: tile = blockIdx.x, blockIdx.x + gridDim.x, ... (barrier phases, the weight ring and the staged
+  // biases carry over from tile to tile; the weight stream of the next tile runs under the tail of this one)
+  const int64_t n_tiles_real = (a.n + TC_M - 1) / TC_M;
+  const int64_t n_tiles = PAIR ? ((n_tiles_real + 1) & ~(int64_t)1) : n_tiles_real;
   // PAIR: two CTAs on neighbouring SMs (a 2-CTA cluster) run their two tiles through the same schedule as ONE
   // M = 256 problem (tcgen05.mma.cta_group::2): each CTA keeps its own rows of A and D in its tensor memory and
   // streams only HALF of every weight stage (N / 2 rows of the hi and lo images) into its shared memory -- the
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     {
       uint32_t s = 0, ph = 0;
       int n_stamp = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
       for (int pass = 0; pass < n_pass; ++pass) {
         const bool inv = (MODE == TC_INV) || (MODE == TC_NF && pass == 0);
         for (int li = 0; li < L; ++li) {
@@ -295,6 +299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     if (PAIR && crank != 0) {
       // peer CTA of a pair: no MMAs to issue; relay the arrival of this CTA's half of every weight stage
       uint32_t s = 0, ph = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
       for (int pass = 0; pass < n_pass; ++pass)
         for (int li = 0; li < L; ++li) {
           const int p = (((MODE == TC_INV) || (MODE == TC_NF && pass == 0)) ? L - 1 - li : li) & 1;
@@ -309,6 +314,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     } else {
       uint32_t s = 0, ph = 0, seq = 0, a_ph = 0;
       int n_stamp = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
       for (int pass = 0; pass < n_pass; ++pass) {
         const bool inv = (MODE == TC_INV) || (MODE == TC_NF && pass == 0);
         for (int li = 0; li < L; ++li) {
@@ -383,8 +389,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     };
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const int64_t grow = row0 + row;
-    const int64_t r = min(grow, a.n - 1);
+    int64_t row0 = 0, grow = 0, r = 0, tile = 0;  // set per tile below
     float* xr = xs + row * xs_stride;
     // Activation image rows of NB (8 or 16) operand columns n0 .. n0 + NB - 1 (NB image rows of 128 B: this warp's
     // 32 samples) -> global.  The 32 lanes write their words into the warp's shared-memory buffer in image order and
@@ -416,6 +421,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     part(g_all, g_lo, g_hi);
     const int j_lo = g_lo * 8, j_hi = min(d, g_hi * 8);
 
+    // stage every layer's biases (once per CTA; visible after the epi_bar that follows).  Flattened over (layer, entry) with 8
+    // independent loads in flight per thread: the naive per-layer loop cost ~16K cycles of serialised L2 latency.
+    {
+      const int total = L * bias_stride;
+      for (int base = 0; base < total; base += 8 * TC_EPI) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = base + u * TC_EPI + tid;
+          v[u] = 0.0f;
+          if (e < total) {
+            const int l = e / bias_stride, c = e - l * bias_stride;
+            const float* PL = P + (int64_t)l * D.layer_stride;
+            if (c < nh * 128) {
+              const int i = c >> 7, cc = c & 127;
+              if (cc < D.dims[i + 1]) v[u] = PL[D.off_b[i] + cc];
+            } else {
+              const int c2 = c - nh * 128, o = c2 / NP, rr = c2 - o * NP, p = l & 1;
+              if (o < (d - p + 1) / 2) v[u] = PL[D.off_b[nh] + (p + 2 * o) * NP + rr];
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = base + u * TC_EPI + tid;
+          if (e < total) sbias_all[e] = v[u];
+        }
+      }
+    }
+    epi_bar();
+    uint32_t seq = 0;
+    int n_stamp = (tid == 0) ? 0 : 256;
+    for (tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    row0 = tile * TC_M;
+    grow = row0 + row;
+    r = min(grow, a.n - 1);
     // ---- load / generate the tile ------------------------------------------------------------
     if (MODE == TC_NF) {
       const int64_t c = r / a.n_steps;
@@ -449,35 +490,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
         xr[j] = v;
       }
     }
-    // stage every layer's biases (visible after the first epi_bar below).  Flattened over (layer, entry) with 8
-    // independent loads in flight per thread: the naive per-layer loop cost ~16K cycles of serialised L2 latency.
-    {
-      const int total = L * bias_stride;
-      for (int base = 0; base < total; base += 8 * TC_EPI) {
-        float v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = base + u * TC_EPI + tid;
-          v[u] = 0.0f;
-          if (e < total) {
-            const int l = e / bias_stride, c = e - l * bias_stride;
-            const float* PL = P + (int64_t)l * D.layer_stride;
-            if (c < nh * 128) {
-              const int i = c >> 7, cc = c & 127;
-              if (cc < D.dims[i + 1]) v[u] = PL[D.off_b[i] + cc];
-            } else {
-              const int c2 = c - nh * 128, o = c2 / NP, rr = c2 - o * NP, p = l & 1;
-              if (o < (d - p + 1) / 2) v[u] = PL[D.off_b[nh] + (p + 2 * o) * NP + rr];
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = base + u * TC_EPI + tid;
-          if (e < total) sbias_all[e] = v[u];
-        }
-      }
-    }
     // the tile (all rows, complete after an epi_bar) -> save_x[slot]: rows are contiguous in global memory, so the
     // CTA writes them as one coalesced stream
     auto save_tile = [&](int slot) {
@@ -489,8 +501,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
       }
     };
     float ldacc = 0.0f;
-    uint32_t seq = 0;
-    int n_stamp = (tid == 0) ? 0 : 256;
     TC_STAMP(2);  // tile loaded
     if (MODE == TC_TRAIN) epi_bar();  // save_tile(0) reads every thread's part of the tile
 
@@ -527,7 +537,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
             if (MODE == TC_TRAIN && a.act_img != nullptr && row0 < a.n) {
               const int npx = tc_pad16(d);
               dump_rows(std::integral_constant<int, 8>{}, hi, lo, g * 8,
-                        a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) + (size_t)q * 2 * npx * 128, npx);
+                        a.act_img + (tile * L + l) * tc_act_layer_bytes(D) + (size_t)q * 2 * npx * 128, npx);
             }
           }
           if (hf == 0) ldacc += inv ? -(float)d * scale : (float)d * scale;
@@ -567,7 +577,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
                     a.save_h[((int64_t)(l * nh + it.lin) * 128 + c + u) * a.n + grow] = hv;
                 }
                 if (MODE == TC_TRAIN && a.act_img != nullptr && row0 < a.n) {
-                  uint8_t* gimg = a.act_img + ((int64_t)blockIdx.x * L + l) * tc_act_layer_bytes(D) +
+                  uint8_t* gimg = a.act_img + (tile * L + l) * tc_act_layer_bytes(D) +
                                   tc_act_item_off(D, it.lin + 1) + (size_t)q * 2 * N * 128;
                   dump_rows(std::integral_constant<int, 16>{}, hi, lo, c, gimg, N);
                 }
@@ -679,6 +689,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
         }
       }
     }
+    epi_bar();  // the tile in shared memory is free for the next one
+    }  // tiles
     if (MODE == TC_TRAIN && a.act_img != nullptr && lane == 0) tc::bulk_wait<0>();  // this lane's bulk stores have landed
     tc::tc_fence_before();
   }
@@ -708,12 +720,19 @@ static int launch_tc_impl(const FlowmcFlowDesc& D, const TcProgram& PR, const Tc
     configured = bytes;
   }
   const unsigned tiles = (unsigned)((a.n + TC_M - 1) / TC_M);
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+  }
+  const unsigned persistent = (unsigned)(PAIR ? (n_sm & ~1) : n_sm);  // one CTA per SM (shared memory allows no more)
   cudaError_t e;
   if (PAIR) {
     // 2-CTA clusters: consecutive tiles pair up (an odd tile count gets one idle partner: its rows clamp to the last
     // row and nothing of it is stored)
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((tiles + 1u) & ~1u);
+    cfg.gridDim = dim3(((tiles + 1u) & ~1u) < persistent ? ((tiles + 1u) & ~1u) : persistent);
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = bytes;
     cfg.stream = stream;
@@ -726,7 +745,7 @@ static int launch_tc_impl(const FlowmcFlowDesc& D, const TcProgram& PR, const Tc
     cfg.numAttrs = 1;
     e = cudaLaunchKernelEx(&cfg, kern, D, PR, b);
   } else {
-    kern<<<tiles, TC_THREADS, bytes, stream>>>(D, PR, b);
+    kern<<<tiles < persistent ? tiles : persistent, TC_THREADS, bytes, stream>>>(D, PR, b);
     e = cudaSuccess;
   }
   flowmc_count_launch();
