@@ -85,6 +85,15 @@ def main():
     x0 = frandom.normal(sub, (n_chains, d), device=dev)
     if shard is not None:
         x0 = shard.slab(x0).contiguous()
+    # warm-up: a miniature run of the same bundle (same target, dimension and flow shape, 256 chains) so that CUDA's
+    # lazy module loading (~50 ms for the first launch of each kernel) and the NCCL communicators are not timed
+    wcfg = dict(cfg, n_training_loops=1, n_production_loops=1, n_epochs=1, batch_size=128, n_max_examples=256)
+    wshard = ChainShard(256 * world, rank, world) if world > 1 else None
+    wx0 = frandom.normal(frandom.PRNGKey(1), (256 * world, d), device=dev)
+    wbundle = RQSpline_MALA_Bundle(frandom.PRNGKey(2), 256 * world, d, target, chain_shard=wshard, **wcfg)
+    Sampler(d, 256 * world, frandom.PRNGKey(3), resource_strategy_bundles=wbundle).sample(
+        wshard.slab(wx0).contiguous() if wshard is not None else wx0, {})
+    del wbundle
     key, sub = frandom.split(key)
     bundle = RQSpline_MALA_Bundle(sub, n_chains, d, target, chain_shard=shard, **cfg)
     acc = {}
