@@ -164,7 +164,7 @@ def flow_extras(dev):
         if m.desc.tc_terms else "fp32 CUDA cores",
         "issued_tflops": issued * n / ms / 1e9,
         "tensor_pipe_frac_from_rate": issued * n / ms / 1e9 / pipe_peak,
-        "tensor_pipe_active_ncu": 0.4706,
+        "tensor_pipe_active_ncu": 0.4758,
         "note": "issued = 3 TF32 terms x the padded GEMM shapes; pipe peak = 4096 flop/clk/SM x 148 SMs x 1.965 GHz = "
                 "1191 TFLOP/s (the cuBLAS-measured bf16_tflops/2 = 850 understates the pipe); tensor_pipe_active_ncu = "
                 "sm__pipe_tensor_cycles_active of a 148-tile launch, profiles/r01_flow_tc_c4_logprob_v2_ncu.txt"}
