@@ -19,7 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from oracle import flow as oflow, local as olocal, nf, rng, targets as otargets  # noqa: E402
+from oracle import flow as oflow, local as olocal, nf, optimization as oopt  # noqa: E402
+from oracle import parallel_tempering as opt_pt, rng, targets as otargets  # noqa: E402
 from flowutil import random_params  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
@@ -85,8 +86,32 @@ def rng_case():
                         permutation=rng.permutation(key, 2000), choice=rng.choice_with_replacement(key, 1000, 64))
 
 
+def strategies_case():
+    """AdamOptimization and ParallelTempering on the reference's own test set-up
+    (test/unit/test_strategies.py:27-78, 337-392)."""
+    key = rng.PRNGKey(42)
+    key, sub = rng.split(key)
+    x0 = (rng.normal(sub, (20, 2)) * 1 + 10).astype(np.float32)
+    data2 = otargets.IsoGaussian.pack(2, 0.5, np.arange(2))
+    a_key, a_x, a_lp = oopt.adam_optimize(key, "iso_gaussian", data2, x0, n_steps=100, learning_rate=5e-2, noise_level=0.0)
+    n_key, n_x, n_lp = oopt.adam_optimize(key, "iso_gaussian", data2, x0, n_steps=30, learning_rate=1e-2, noise_level=10.0,
+                                          bounds=[[9.0, 10.5]])
+    key = rng.PRNGKey(42)
+    key, sub = rng.split(key)
+    p0 = rng.normal(sub, (7, 3))
+    key, sub = rng.split(key)
+    tp = rng.normal(sub, (7, 4, 3))
+    temps = (np.arange(5) + 1.0).astype(np.float32)
+    data3 = otargets.IsoGaussian.pack(3, 0.5, np.arange(3))
+    pt_key, pt_p0, pt_tp, pt_t, pt_acc = opt_pt.parallel_tempering(key, p0, tp, temps, "iso_gaussian", data3, 4, 1.0)
+    np.savez_compressed(os.path.join(OUT, "strategies_iso.npz"), adam_key=a_key, adam_x0=x0, adam_x=a_x, adam_lp=a_lp,
+                        adam_noisy_key=n_key, adam_noisy_x=n_x, adam_noisy_lp=n_lp, pt_key_in=key, pt_x0=p0,
+                        pt_tempered_in=tp, pt_key=pt_key, pt_positions=pt_p0, pt_tempered=pt_tp,
+                        pt_temperatures=pt_t, pt_accepts=pt_acc)
+
+
 if __name__ == "__main__":
-    flow_case(); init_case(); local_case(); nf_case(); rng_case()
+    flow_case(); init_case(); local_case(); nf_case(); rng_case(); strategies_case()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -103,3 +103,19 @@ def test_chain_sharding_is_bit_identical(cuda):
         k, x, lp = part.optimize(key, None, x0[a:b], data)
         assert np.array_equal(k, k_full)
         assert torch.equal(x, x_full[a:b]) and torch.equal(lp, lp_full[a:b])
+
+
+def test_matches_the_committed_golden_vectors(cuda):
+    """The device path against tests/golden/strategies_iso.npz (frozen oracle outputs on the reference's test set-up)."""
+    import os
+    from flowmc_b200 import random as frandom
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "strategies_iso.npz"))
+    key = frandom.split(frandom.PRNGKey(42))[0]
+    data = {"data": np.arange(2, dtype=np.float32)}
+    k, x, lp = _strategy().optimize(key, None, torch.from_numpy(g["adam_x0"]).cuda(), data)
+    assert np.array_equal(k, g["adam_key"])
+    assert_close(x.cpu().numpy(), g["adam_x"], "adam positions", rtol=3e-4)
+    assert_close(lp.cpu().numpy(), g["adam_lp"], "adam log-prob", rtol=3e-4)
+    k, x, lp = _strategy(n_steps=30, learning_rate=1e-2, noise_level=10.0, bounds=np.array([[9.0, 10.5]])).optimize(
+        key, None, torch.from_numpy(g["adam_x0"]).cuda(), data)
+    assert_close(x.cpu().numpy(), g["adam_noisy_x"], "noisy adam positions", rtol=3e-4)

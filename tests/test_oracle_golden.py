@@ -207,3 +207,27 @@ def test_parallel_tempering_restatement_invariants():
     # not training: buffers untouched
     _, _, tpos_nt, t_nt, _ = opt.parallel_tempering(key, x0, tp, temps, "iso_gaussian", data, 4, 1.0, training=False)
     assert np.array_equal(tpos_nt, tp) and np.array_equal(t_nt, temps)
+
+
+def test_strategies_golden():
+    """oracle AdamOptimization / ParallelTempering against the committed vectors (tests/golden/strategies_iso.npz)."""
+    from oracle import optimization as oopt, parallel_tempering as opt_pt, targets as O
+    from oracle import rng as orng
+    g = _load("strategies_iso.npz")
+    key = orng.split(orng.PRNGKey(42))[0]
+    d2 = O.IsoGaussian.pack(2, 0.5, np.arange(2))
+    k, x, lp = oopt.adam_optimize(key, "iso_gaussian", d2, g["adam_x0"], n_steps=100, learning_rate=5e-2, noise_level=0.0)
+    assert np.array_equal(k, g["adam_key"])
+    np.testing.assert_allclose(x, g["adam_x"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(lp, g["adam_lp"], rtol=1e-6, atol=1e-5)
+    k, x, lp = oopt.adam_optimize(key, "iso_gaussian", d2, g["adam_x0"], n_steps=30, learning_rate=1e-2, noise_level=10.0,
+                                  bounds=[[9.0, 10.5]])
+    np.testing.assert_allclose(x, g["adam_noisy_x"], rtol=1e-6, atol=1e-6)
+    d3 = O.IsoGaussian.pack(3, 0.5, np.arange(3))
+    temps = (np.arange(5) + 1.0).astype(np.float32)
+    k, p0, tp, t, acc = opt_pt.parallel_tempering(g["pt_key_in"], g["pt_x0"], g["pt_tempered_in"], temps, "iso_gaussian",
+                                                  d3, 4, 1.0)
+    assert np.array_equal(k, g["pt_key"]) and np.array_equal(acc, g["pt_accepts"])
+    np.testing.assert_allclose(p0, g["pt_positions"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(tp, g["pt_tempered"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(t, g["pt_temperatures"], rtol=1e-6)
