@@ -199,6 +199,56 @@ def flow_extras(dev):
     return out
 
 
+def local_extras(dev):
+    """Device-timed local-step calls of the other BASELINE.json local configs (C3 HMC, the local phase of C5); reported
+    under "extra" next to the headline C2 metric."""
+    import torch
+    from flowmc_b200 import random as frandom, targets as T
+    from flowmc_b200.resource.buffers import Buffer
+    from flowmc_b200.resource.kernel.HMC import HMC
+    from flowmc_b200.resource.kernel.MALA import MALA
+    from flowmc_b200.resource.logPDF import LogPDF
+    from flowmc_b200.resource.states import State
+    from flowmc_b200.strategy.take_steps import TakeSerialSteps
+
+    def run(kernel, target, n, d, steps):
+        res = {"p": Buffer("p", (n, steps, d), 1, device=dev), "l": Buffer("l", (n, steps), 1, device=dev),
+               "a": Buffer("a", (n, steps), 1, device=dev), "s": State({"p": "p", "l": "l", "a": "a"}, "s"),
+               "k": kernel, "logpdf": LogPDF(target, n_dims=d)}
+        strat = TakeSerialSteps("logpdf", "k", "s", ["p", "l", "a"], steps)
+        x0 = frandom.normal(frandom.split(frandom.PRNGKey(0))[1], (n, d), device=dev)
+        best = float("inf")
+        for i in range(4):
+            strat.set_current_position(0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            strat(frandom.PRNGKey(1), res, x0, None)
+            e1.record()
+            torch.cuda.synchronize()
+            if i:
+                best = min(best, e0.elapsed_time(e1))
+        acc = float(res["a"].data.mean())
+        del res
+        return n * steps / best * 1e3, best, acc
+
+    out = {}
+    m = np.linspace(0.5, 2.0, 64).astype(np.float32)
+    rate, ms, acc = run(HMC(np.diag(m), 0.01, 10), T.rosenbrock(), 32768, 64, 200)
+    out["hmc_c3"] = {"chain_steps_per_s": rate, "ms_per_call": ms, "acceptance_rate": acc,
+                     "workload": "C3: 64-D Rosenbrock, 32768 chains, HMC step 0.01, 10 leapfrog steps, diagonal mass, "
+                                 "200 steps per call",
+                     "hbm_frac": rate * 4 * (64 + 2) / 1e9 / measured_peak()[0],
+                     "note": "12 gradient evaluations + 69 threefry blocks per chain-step: fp32 / issue bound"}
+    mu = np.zeros((8, 64), np.float32)
+    for i in range(8):
+        mu[i, i] = 3.0 if i % 2 == 0 else -3.0
+    rate, ms, acc = run(MALA(0.1), T.gaussian_mixture(mu, 1.0), 65536, 64, 50)
+    out["mala_c5_local"] = {"chain_steps_per_s": rate, "ms_per_call": ms, "acceptance_rate": acc,
+                            "workload": "C5 local phase: 64-D 8-component mixture, 65536 chains, MALA 0.1, 50 steps per call",
+                            "hbm_frac": rate * 4 * (64 + 2) / 1e9 / measured_peak()[0]}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -360,6 +410,7 @@ def run_ours(args):
     if os.environ.get("FLOWMC_BENCH_EXTRAS", "1") != "0":
         try:
             extras = flow_extras(dev)
+            extras.update(local_extras(dev))
         except Exception as ex:  # the headline line must still be printed
             extras = {"error": repr(ex)}
     peak, peak_src = measured_peak()
