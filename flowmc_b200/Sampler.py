@@ -1,74 +1,55 @@
-"""Sampler -- top-level API (reference: src/flowMC/Sampler.py:10-118).
+"""Sampler -- the top-level driver (reference: src/flowMC/Sampler.py:10-118).
 
-Pure host orchestration: iterates ``strategy_order`` and threads ``(rng_key, resources,
-last_step)`` through the strategies exactly like the reference (Sampler.py:84-108).
+Host orchestration only: the sampler owns a dict of resources and a dict of strategies and runs the strategies in
+``strategy_order``, handing ``(rng_key, resources, position)`` from one to the next.  Everything that costs time
+happens inside the strategies (one C-ABI call each on the B200 path).
 """
 from __future__ import annotations
 
-from typing import Optional
-
 import torch
 
-from .resource.base import Resource
-from .strategy.base import Strategy
+_SETTINGS = {"verbose": False, "logging": True, "outdir": "./outdir/"}   # keyword overrides the reference accepts
 
 
 class Sampler:
-    # Essential parameters
-    n_dim: int
-    n_chains: int
-    resources: dict
-    strategies: dict
-    strategy_order: Optional[list]
+    def __init__(self, n_dim: int, n_chains: int, rng_key, resources: dict | None = None,
+                 strategies: dict | None = None, strategy_order: list | None = None,
+                 resource_strategy_bundles=None, **kwargs):
+        self.n_dim, self.n_chains, self.rng_key = n_dim, n_chains, rng_key
+        for name, default in _SETTINGS.items():
+            setattr(self, name, kwargs.get(name, default))
 
-    # Logging hyperparameters
-    verbose: bool = False
-    logging: bool = True
-    outdir: str = "./outdir/"
-
-    def __init__(self, n_dim: int, n_chains: int, rng_key, resources=None, strategies=None,
-                 strategy_order=None, resource_strategy_bundles=None, **kwargs):
-        self.n_dim = n_dim
-        self.n_chains = n_chains
-        self.rng_key = rng_key
-
-        if resources is not None and strategies is not None:
+        explicit = resources is not None and strategies is not None
+        if explicit:
             print("Resources and strategies provided. Ignoring resource strategy bundles.")
-            self.resources = resources
-            self.strategies = strategies
-            self.strategy_order = strategy_order
+            source = (resources, strategies, strategy_order)
         else:
             print("Resources or strategies not provided. Using resource strategy bundles.")
             if resource_strategy_bundles is None:
-                raise ValueError(
-                    "Resource strategy bundles not provided."
-                    "Please provide either resources and strategies or resource strategy bundles."
-                )
-            self.resources = resource_strategy_bundles.resources
-            self.strategies = resource_strategy_bundles.strategies
-            self.strategy_order = resource_strategy_bundles.strategy_order
+                raise ValueError("Resource strategy bundles not provided."
+                                 "Please provide either resources and strategies or resource strategy bundles.")
+            b = resource_strategy_bundles
+            source = (b.resources, b.strategies, b.strategy_order)
+        self.resources, self.strategies, self.strategy_order = source
 
-        class_keys = list(self.__class__.__dict__.keys())
-        for key, value in kwargs.items():
-            if key in class_keys and not key.startswith("__"):
-                setattr(self, key, value)
+    def _strategy(self, name: str):
+        try:
+            return self.strategies[name]
+        except KeyError:
+            raise ValueError(f"Invalid strategy name '{name}' provided. "
+                             f"Available strategies are: {list(self.strategies.keys())}.") from None
 
     def sample(self, initial_position, data: dict):
-        initial_position = torch.atleast_2d(torch.as_tensor(initial_position, dtype=torch.float32))
-        rng_key = self.rng_key
-        last_step = initial_position
-        assert isinstance(self.strategy_order, list)
-        for strategy in self.strategy_order:
-            if strategy not in self.strategies:
-                raise ValueError(
-                    f"Invalid strategy name '{strategy}' provided. "
-                    f"Available strategies are: {list(self.strategies.keys())}."
-                )
-            rng_key, self.resources, last_step = self.strategies[strategy](
-                rng_key, self.resources, last_step, data
-            )
-        self.rng_key = rng_key
-        self.last_step = last_step
+        """Run every strategy of ``strategy_order`` once, in order (Sampler.py:84-108).  ``initial_position`` is
+        ``[n_chains, n_dim]`` (a single position is promoted to one chain); the last strategy's position is kept in
+        ``last_step``, the advanced key in ``rng_key``."""
+        if not isinstance(self.strategy_order, list):
+            raise AssertionError("strategy_order must be a list of strategy names")
+        position = torch.atleast_2d(torch.as_tensor(initial_position, dtype=torch.float32))
+        key = self.rng_key
+        for name in self.strategy_order:
+            key, self.resources, position = self._strategy(name)(key, self.resources, position, data)
+        self.rng_key, self.last_step = key, position
 
     def serialize(self):
         raise NotImplementedError
