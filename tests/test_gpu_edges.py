@@ -96,3 +96,26 @@ def test_global_step_single_proposal(cuda):
         assert torch.isinf(res["a"].data[:, 1]).all()          # the untouched slot keeps the -inf fill (buffers.py:27)
         stay = acc == 0
         assert torch.equal(last[stay], x0[stay])
+
+
+@pytest.mark.parametrize("d,hidden", [(130, [64, 64]), (6, [40, 24])])
+def test_shapes_outside_the_tensor_core_path_fall_back_to_cuda_cores(cuda, monkeypatch, d, hidden):
+    """n_features > 128 or hidden widths that are not multiples of 16: forward, sampling and a training step run on the
+    fp32 CUDA-core kernels (chosen per model) even though the tensor-core path is requested."""
+    from oracle import flow as oflow, nf
+    monkeypatch.setenv("FLOWMC_FLOW_TC", "3")
+    p = random_params(13, d, 2, hidden, 8, gain=1.5)
+    m = model_from_params(p)
+    r = np.random.default_rng(d)
+    x = (1.5 * r.standard_normal((70, d))).astype(np.float32)
+    lp = m.log_prob(torch.from_numpy(x).cuda())
+    o32 = oflow.log_prob(p, x)
+    with oflow.precision(np.float64):
+        o64 = oflow.log_prob(p, x)
+    assert_close(lp.cpu().numpy(), o32, "log_prob", floor=o32 - o64, floor_factor=3.0)
+    loss, grad = m.loss_and_grad(torch.from_numpy(x).cuda())
+    o_loss, _ = nf.loss_and_grads(p, x)
+    assert abs(float(loss) - o_loss) <= 1e-5 * max(1.0, abs(o_loss))
+    assert bool(torch.isfinite(grad).all()) and float(grad.abs().max()) > 0
+    from oracle import rng
+    assert m.sample(rng.PRNGKey(2), 33).shape == (33, d)
