@@ -17,9 +17,13 @@
 //     chunk of 4 features (100 of 112 columns) is read back with tcgen05.ld (TMEM lane = sample) and softmax /
 //     cumsum / softplus / bin search / transform / log-det run in registers (flow_common.cuh), exactly the code the
 //     CUDA-core path uses.  Only the transformed half of W3 is ever loaded.
-//   * warp roles: warps 0-15 epilogue (TC_PARTS = 4 threads per sample row, splitting columns / features: four
-//     warps per scheduler hide the MUFU / TMEM latencies of the spline chains), warp 16 weight producer (one elected
-//     lane issues the bulk copies), warp 17 MMA issuer (one elected lane).
+//   * warp roles: warps 0-7 epilogue (TC_PARTS = 2 threads per sample row, splitting columns / features; a warp can
+//     only touch its own quarter of the TMEM lanes), warp 8 weight producer, warp 9 MMA issuer (whole warps walk the
+//     schedule, one elected lane issues);
+//   * hand-offs: per K-chunk of 32 operand columns (a_ready[4], one arrival per epilogue warp), so a GEMM starts on
+//     its first chunk while the tanh epilogue is still producing the later ones; persistent CTAs loop over tiles;
+//     TRAIN mode also leaves the layer inputs, the spline parameters and packed activation images (through
+//     shared-memory staging + bulk stores) for the backward pass; PAIR mode = CTA pairs (cta_group::2), optional.
 //   TMEM map (512 columns): [0,128) A hi | [128,256) A lo | [256,384) acc slot 0 | [384,512) acc slot 1.
 #include <cstdlib>
 #include <cstring>

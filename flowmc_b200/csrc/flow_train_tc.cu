@@ -12,13 +12,15 @@
 //                                              the conditioner input and hidden activations straight into the packed
 //                                              B-stage layout (flow_tc.cuh: tc_act_*), so no recompute and no
 //                                              re-layout pass
-//   the dW tile (lane = output unit) is read back with tcgen05.ld and reduced over tiles with red.global.add.f32.
+//   the dW tile (lane = output unit) is read back with tcgen05.ld and stored into this CTA's private, permuted
+//   accumulator; the accumulators are summed in CTA order by reducer CTAs inside the same launch (no atomics).
 //
 // One CTA = 128 samples, layers in reverse.  Per layer: for every chunk of 4 transformed features
 // {spline adjoints -> dtheta; dh_last += dtheta W3_c (acc slot 0); dW3_c = dtheta^T h_last (acc slot 1)}, then per
 // tanh layer {da = dh (1 - h^2); dh_prev = da W; dW = da^T h_prev}, masked-coupling and ScalarAffine adjoints.
-// Epilogue and MMA strictly alternate (they share the A region of tensor memory); the weight producer prefetches
-// the next items' stages through a 3-deep ring meanwhile.
+// The epilogue is software-pipelined against the MMA warp (see the kernel: adjoints of unit u+1 under the weight-
+// gradient MMAs of unit u, dW store of unit u-1 under the data-gradient MMAs of unit u); the weight producer
+// prefetches the next items' stages through a 3-deep ring meanwhile.
 // TMEM map: [0,128) A hi | [128,256) A lo | [256,384) acc 0 (data gradient) | [384,512) acc 1 (weight gradient).
 #include <cstring>
 #include <string>
