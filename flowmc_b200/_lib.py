@@ -75,6 +75,7 @@ def _load() -> C.CDLL:
         "flowmc_target_name": (C.c_char_p, [i32]),
         "flowmc_target_eval": (i32, [i32, vp, vp, i64, i32, vp, vp, vp]),
         "flowmc_key_split": (i32, [u32p, i64, u32p]),
+        "flowmc_key_split_batch": (i32, [u32p, i64, i64, u32p]),
         "flowmc_random_bits": (i32, [u32p, i64, vp, vp]),
         "flowmc_random_uniform": (i32, [u32p, i64, f32, f32, vp, vp]),
         "flowmc_random_normal": (i32, [u32p, i64, vp, vp]),

@@ -167,6 +167,19 @@ int flowmc_key_split(const uint32_t key[2], int64_t num, uint32_t* out) {
   return FLOWMC_OK;
 }
 
+int flowmc_key_split_batch(const uint32_t* keys, int64_t n_keys, int64_t num, uint32_t* out) {
+  if (!keys || !out || n_keys < 0 || num < 0) return fail(FLOWMC_ERR_INVALID, "key_split_batch: bad arguments");
+  for (int64_t c = 0; c < n_keys; ++c) {
+    const flowmc::Key k{keys[2 * c], keys[2 * c + 1]};
+    for (int64_t i = 0; i < num; ++i) {
+      const flowmc::Key r = flowmc::split_at(k, (uint64_t)i);
+      out[2 * (c * num + i)] = r.k0;
+      out[2 * (c * num + i) + 1] = r.k1;
+    }
+  }
+  return FLOWMC_OK;
+}
+
 int flowmc_random_bits(const uint32_t key[2], int64_t n, uint32_t* out, void* stream) {
   if (!key || n < 0 || (n > 0 && !out)) return fail(FLOWMC_ERR_INVALID, "random_bits: bad arguments");
   if (n == 0) return FLOWMC_OK;

@@ -34,6 +34,14 @@ def PRNGKey(seed: int) -> np.ndarray:
 key = PRNGKey
 
 
+def split_each(keys: np.ndarray, num: int = 2) -> np.ndarray:
+    """``jax.vmap(lambda k: jax.random.split(k, num))(keys)``: keys [n, 2] -> [n, num, 2] (one C call)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint32).reshape(-1, 2)
+    out = np.empty((keys.shape[0], num, 2), dtype=np.uint32)
+    check(lib.flowmc_key_split_batch(keys.ctypes.data_as(_u32p), keys.shape[0], num, out.ctypes.data_as(_u32p)))
+    return out
+
+
 def split(key: np.ndarray, num: int = 2) -> np.ndarray:
     k, kp = _kp(key)
     out = np.empty((num, 2), dtype=np.uint32)

@@ -86,7 +86,7 @@ class ParallelTempering(Strategy):
         dev = positions.device
         offset, n_glob = self.chain_shard if self.chain_shard is not None else (0, n)
         chain_keys = frandom.split(subkey, n_glob)[offset:offset + n]                       # :98
-        keys = np.stack([frandom.split(k, n_temps) for k in chain_keys]).reshape(n * n_temps, 2)   # :283
+        keys = frandom.split_each(chain_keys, n_temps).reshape(n * n_temps, 2)               # :283
         keys_d = torch.from_numpy(np.ascontiguousarray(keys).view(np.int32)).to(dev)
         temps = torch.as_tensor(temperatures, dtype=torch.float32, device=dev).reshape(n_temps)
         beta = (1.0 / temps).repeat(n).contiguous()                                         # logPDF.py:106

@@ -74,6 +74,8 @@ FLOWMC_API int flowmc_target_eval(int target_id, const float* data, const float*
 /* ---- jax.random-compatible key management (host, synchronous, tiny) ---- */
 /* split(key, num) -> out host uint32[num][2] */
 FLOWMC_API int flowmc_key_split(const uint32_t key[2], int64_t num, uint32_t* out);
+/* vmapped split: out[c, i] = jax.random.split(keys[c], num)[i]; keys host [n_keys, 2], out host [n_keys, num, 2] */
+FLOWMC_API int flowmc_key_split_batch(const uint32_t* keys, int64_t n_keys, int64_t num, uint32_t* out);
 /* ---- jax.random-compatible draws written to device memory ---- */
 FLOWMC_API int flowmc_random_bits(const uint32_t key[2], int64_t n, uint32_t* out, void* stream);
 FLOWMC_API int flowmc_random_uniform(const uint32_t key[2], int64_t n, float minval, float maxval, float* out, void* stream);
