@@ -166,7 +166,8 @@ __device__ __forceinline__ void bt_reduce_layer(const FlowmcFlowDesc& D, const f
 __device__ __forceinline__ float bt_reduce_loss(const float* partial, int64_t pstride, int n_cta);
 
 struct BtSmem {
-  uint64_t stage_full[BT_STAGES], stage_empty[BT_STAGES], acc_full, a_ready;
+  uint64_t stage_full[BT_STAGES], stage_empty[BT_STAGES], acc_full;
+  uint64_t a_ready[4];  // per K-chunk (32 columns) of the A operand, one arrival per epilogue warp
   uint32_t tmem_base;
   float red[2 * TC_EPI_WARPS];
   float bsum[TC_PARTS][TC_M];
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
       tc::mbar_init(&S->stage_empty[i], 1);
     }
     tc::mbar_init(&S->acc_full, 1);
-    tc::mbar_init(&S->a_ready, TC_EPI);
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&S->a_ready[i], TC_EPI_WARPS);
     tc::fence_mbar_init();
   }
   if (warp == TC_EPI_WARPS) tc::tmem_alloc<512>(&S->tmem_base);
@@ -237,14 +238,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
       const int p = l & 1;
       for (int ii = 0; ii < PR.n_items[p]; ++ii) {
         const BtItem it = PR.items[p][ii];
-        tc::mbar_wait(&S->a_ready, a_ph);  // the epilogue has written this item's A operand
-        a_ph ^= 1;
-        tc::tc_fence_after();
+        // (the epilogue signals the item's A operand K-chunk by K-chunk, see below)
         const bool wg = (it.kind == BK_WG3) || (it.kind == BK_WGH);
         const uint32_t t_acc = tbase + (wg ? 384 : 256);
         const uint32_t idesc = tc::make_idesc_tf32(TC_M, it.N);
         const bool cont = (it.kind == BK_DG3) && (it.lin > 0);  // later chunks accumulate into dh_last
         for (int kc = 0; kc < it.n_kc; ++kc) {
+          tc::mbar_wait(&S->a_ready[kc], (a_ph >> kc) & 1);  // K-chunk kc of the A operand is written
+          a_ph ^= 1u << kc;
           tc::mbar_wait(&S->stage_full[s], ph);
           tc::tc_fence_after();
           const uint32_t b_hi = tc::smem_u32(stages + (size_t)s * TC_STAGE_BYTES);
@@ -289,43 +290,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
     // ---- software pipeline -------------------------------------------------------------------------
     // A "unit" is one (data-gradient, weight-gradient) pair of GEMMs: a chunk of spline features, or one tanh
     // layer.  For unit u the epilogue threads
-    //   [A] write the prepared dY rows as the A operand                      -> dgrad MMAs of u start
-    //   [B] read dY back TRANSPOSED from shared memory into registers   }
-    //   [C] store the dW tile of unit u-1 (acc 1) into the accumulator  }    overlap the dgrad MMAs
+    //   [F] compute dY of u (spline adjoints / tanh derivative; at a layer boundary first the masked-coupling and
+    //       ScalarAffine adjoints)                                 -- under the wgrad MMAs of u-1
+    //   [G] wait for those MMAs (the A region of tensor memory is theirs until then): normally free by now
+    //   [A] write dY as the A operand straight from the registers, K-chunk by K-chunk (a_ready[kc]): the dgrad MMAs
+    //       of u start on the first features while the later ones are still in [F]
+    //   [C] store the dW tile of u-1 (acc 1) into the accumulator  -- under the dgrad MMAs of u
     //   [D] wait for the dgrad MMAs
-    //   [E] write dY^T as the A operand                                      -> wgrad MMAs of u start
-    //   [F] prepare unit u+1 (spline adjoints / tanh derivative; at a layer boundary first the masked-coupling
-    //       and ScalarAffine adjoints)                                       overlaps the wgrad MMAs
-    //   [G] wait for the wgrad MMAs.
-    // The A region of tensor memory is the only resource epilogue and MMA hand back and forth.
-    auto arrive_item = [&]() {
-      tc::tmem_wait_st();
-      tc::tc_fence_before();
-      tc::mbar_arrive(&S->a_ready);
+    //   [E] read dY back TRANSPOSED from shared memory and write it as the A operand -> wgrad MMAs of u start.
+    // whole warps call this after every lane has written (and fenced) its part of K-chunk kc: one arrival per warp
+    auto arrive_chunk = [&](int kc) {
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&S->a_ready[kc]);
     };
     auto wait_item = [&]() {
       tc::mbar_wait(&S->acc_full, f_ph);
       f_ph ^= 1;
       tc::tc_fence_after();
     };
-    // dY of this thread's row: two segments of up to 32 A columns each.  prepare() leaves the values in the
-    // transpose buffer (T[column][row], written by this same thread), write_arow() moves them into the A region.
-    int seg_base[2], seg_len[2];
-    auto write_arow = [&]() {
+    // 8 consecutive A columns of this thread's row, from registers
+    auto write_a8 = [&](int col, const float* v) {
+      uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int sg = 0; sg < 2; ++sg) {
-#pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-          if (c < seg_len[sg]) {
-            uint32_t hi[8], lo[8];
-            const float* src = T + (seg_base[sg] + c) * BT_TS + t;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) tc::split_tf32(src[u * BT_TS], hi[u], lo[u]);
-            tc::tmem_st8(t_ahi + lane_base + seg_base[sg] + c, hi);
-            tc::tmem_st8(t_alo + lane_base + seg_base[sg] + c, lo);
-          }
-        }
-      }
+      for (int u = 0; u < 8; ++u) tc::split_tf32(v[u], hi[u], lo[u]);
+      tc::tmem_st8(t_ahi + lane_base + col, hi);
+      tc::tmem_st8(t_alo + lane_base + col, lo);
     };
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += a.n_cta) {
     const bool first = tile == (int64_t)blockIdx.x;  // first tile of this CTA: store, later tiles: accumulate
@@ -359,38 +348,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
     epi_bar();
     if (tid == 0) acc_to(PB + a.pstride - 4, (S->red[0] + S->red[1]) + (S->red[2] + S->red[3]));
 
-    // dY of the unit (layer l, items ii / ii + 1) -> the transpose buffer T[column][row] + this row's A segments
-    auto prepare = [&](int l, int ii) {
+    // dY of the unit (layer l, items ii / ii + 1): into the transpose buffer T[column][row] (for the weight-gradient
+    // operand) AND, straight from the registers, into the A region (lane = this row) for the data-gradient GEMM.
+    // The A region is still being read by the previous unit's weight-gradient MMAs while the adjoints are computed:
+    // the wait for them ([G], need_g) sits right before the first A write, where it is normally free.  Spline chunks
+    // hand their operand over feature by feature (K-chunk = one feature's 32-column slot; features alternate between
+    // the row's two threads), so the MMAs of the first features run under the adjoints of the later ones.  tanh units
+    // read the previous data gradient from acc 0, which their own GEMM overwrites: all chunks at the end.
+    auto prepare = [&](int l, int ii, bool need_g) {
       const int p = l & 1;
       const BtItem it = PR.items[p][ii];
       const float* PL = P + (int64_t)l * D.layer_stride;
-      seg_len[0] = seg_len[1] = 0;
-      seg_base[0] = seg_base[1] = 0;
+      bool g_pending = need_g;
       if (it.kind == BK_DG3) {
         const float shift = PL[D.off_shift], e = expf(PL[D.off_scale]);
         const float* xin = a.save_x + ((int64_t)l * n + r) * d;
-        int i_lo, i_hi;
-        part(it.n_feat, i_lo, i_hi);
+        // chunks owned by the row's other thread: nothing to add
+        for (int kc = 1 - hf; kc < it.n_feat; kc += 2) arrive_chunk(kc);
 #pragma unroll
         for (int sg = 0; sg < 2; ++sg) {
-          const int fi = i_lo + sg;
-          if (fi < i_hi) {
+          const int fi = 2 * sg + hf;
+          if (fi < it.n_feat) {
             const int fo = it.lin + fi, f = p + 2 * fo;
-            float raw[NP], dr[NP], gx;
+            float raw[NP], dr[32], gx;
             const float* th = a.save_theta + ((int64_t)l * ((d + 1) / 2) + fo) * NP * n + r;
 #pragma unroll
             for (int u = 0; u < NP; ++u) raw[u] = th[(int64_t)u * n];
             const float xa = (xin[f] + shift) * e;
             rq_backward<KB, true>(raw, D.range_min, D.range_max, xa, gr[f], gld, gx, dr);
             gr[f] = gx;
-            seg_base[sg] = fi * 32;
-            seg_len[sg] = 32;
 #pragma unroll
-            for (int u = 0; u < 32; ++u) {
-              T[(fi * 32 + u) * BT_TS + t] = (u < NP) ? dr[u < NP ? u : 0] : 0.0f;
+            for (int u = NP; u < 32; ++u) dr[u] = 0.0f;
+#pragma unroll
+            for (int u = 0; u < 32; ++u) T[(fi * 32 + u) * BT_TS + t] = dr[u];
+            if (g_pending) {
+              wait_item();
+              g_pending = false;
             }
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) write_a8(fi * 32 + c, dr + c);
+            tc::tmem_wait_st();
+            tc::tc_fence_before();
+            arrive_chunk(fi);
           }
         }
+        if (g_pending) wait_item();
       } else {
         // da = dh (1 - h^2): dh from acc 0, h from the forward pass's activation image (hi + lo)
         const int i = it.lin, N = D.dims[i + 1];
@@ -400,10 +402,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
         int c_lo, c_hi;
         part(N / 16, c_lo, c_hi);
         const int c0 = c_lo * 16, cn = (c_hi - c_lo) * 16;  // this thread's columns [c0, c0 + cn), cn <= 64
-        seg_base[0] = c0;
-        seg_len[0] = min(cn, 32);
-        seg_base[1] = c0 + 32;
-        seg_len[1] = max(0, cn - 32);
         // 16 columns at a time; the activation words of the next group are requested before this group's are
         // consumed (the image comes from L2 / HBM: ~1 us away)
         uint32_t hb[2][32];
@@ -423,14 +421,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
             float v[16];
             tc::tmem_ld16(tbase + 256 + lane_base + c0 + g4 * 16, v);
             tc::tmem_wait_ld();
-
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
               const float hv = __uint_as_float(hb[g4 & 1][u]) + __uint_as_float(hb[g4 & 1][16 + u]);
-              T[(c0 + g4 * 16 + u) * BT_TS + t] = v[u] * (1.0f - hv * hv);
+              v[u] = v[u] * (1.0f - hv * hv);
+              T[(c0 + g4 * 16 + u) * BT_TS + t] = v[u];
             }
+            if (g_pending) {
+              wait_item();
+              g_pending = false;
+            }
+            write_a8(c0 + g4 * 16, v);
+            write_a8(c0 + g4 * 16 + 8, v + 8);
           }
         }
+        if (g_pending) wait_item();
+        tc::tmem_wait_st();
+        tc::tc_fence_before();   // (also orders this thread's acc 0 reads before the GEMM that overwrites acc 0)
+        for (int kc = 0; kc < it.n_kc; ++kc) arrive_chunk(kc);
       }
     };
     // the unit after (l, ii): pull the spline parameters its prepare() will read (HBM, written by the forward pass)
@@ -567,15 +575,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
     while (true) {
       const bool have = l >= 0;
       if (pl >= 0 && (!have || l != pl)) finish_layer(pl);  // [F] layer boundary: needs the dgrad of the last unit
-      if (have) prepare(l, ii);                             // [F] overlaps the wgrad MMAs of the previous unit
+      if (have) prepare(l, ii, pl >= 0);                    // [F] + [G] + [A]: overlaps the previous unit's wgrad MMAs,
+      else if (pl >= 0) wait_item();                        //   hands the dgrad operand over chunk by chunk
       BT_STAMP();
-      if (pl >= 0) wait_item();                             // [G] wgrad of the previous unit done
-      BT_STAMP();
-      if (have) {
-        write_arow();                                       // [A] -> dgrad MMAs start
-        arrive_item();
-        prefetch_next(l, ii);
-      }
+      if (have) prefetch_next(l, ii);
       if (pl >= 0) reduce_unit(pl, pii);                    // [C] overlaps the dgrad MMAs
       if (last && a.done != nullptr) {
         // Layer pl of this CTA's accumulator is final after the store above: publish it to the reducer CTAs -- one
@@ -620,7 +623,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
         }
         S->bsum[hf][t] = bsum;
       }
-      arrive_item();                                        // -> wgrad MMAs start
+      tc::tmem_wait_st();
+      tc::tc_fence_before();
+      for (int kc = 0; kc < 4; ++kc) arrive_chunk(kc);      // -> wgrad MMAs start (K = the tile's 128 rows)
       epi_bar();                                            // T free for the next unit's prepare; bsum visible
       BT_STAMP();
       pl = l;
