@@ -1,18 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the flowMC sampling hot path on B200.
 
-Workload (BASELINE.json configs[1], the config the chain-steps/s metric is quoted on and the
-largest local-step config that is defined for one GPU): 128-D AR(1)-correlated Gaussian,
-8192 chains per GPU, MALA step_size=0.1, one "step" = one TakeSerialSteps call of 1000 MALA
-steps for every chain (8.192 M chain-steps, 4.26 GB of samples written, >> the 126 MB L2, so no
-L2 flush is needed between steps).
+Headline workload (BASELINE.json configs[1], the config the chain-steps/s metric is quoted on and the largest
+local-step config that is defined for one GPU): 128-D AR(1)-correlated Gaussian, 8192 chains per GPU, MALA
+step_size=0.1, one "step" = one TakeSerialSteps call of 1000 MALA steps for every chain (8.192 M chain-steps, 4.26 GB
+of samples written, >> the 126 MB L2, so no L2 flush is needed between steps).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-N > 1 is launched by torchrun (one rank per GPU); chains shard across ranks with no
-communication on the data path (weak scaling: 8192 chains per GPU, global chain index keys).
-Rank 0 prints ONE JSON line.  `--impl reference` times the CPU stand-in for the reference (the C
-restatement under oracle/, all host threads) on a bounded sample of the same workload.
+N > 1 is launched by torchrun (one rank per GPU).  The headline shards chains across ranks with no communication on
+the data path (weak scaling: 8192 chains per GPU, global chain index keys).  The paths that DO communicate are
+measured in the same process on the same N ranks and reported under "scaled": the full C5 Sampler (65536 chains in
+total, strong scaling: chain shards + all-gather of the training set + data-parallel flow training with a gradient
+all-reduce per step) and the C4 data-parallel flow-training step.  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the CPU stand-in for the reference (the C restatement under oracle/, all host threads, set
+explicitly because torchrun exports OMP_NUM_THREADS=1) on the same config: every step is the full 8192 chains x 1000
+MALA steps.
 """
 from __future__ import annotations
 
@@ -35,10 +39,16 @@ N_LOCAL_STEPS = 1000
 STEP_SIZE = 0.1
 RHO = 0.9
 BYTES_PER_CHAIN_STEP = 4 * (D + 2)  # position (d fp32) + log-prob + accept flag, SURVEY.md 8(d)
-# from the committed ncu --set full capture of this kernel at this workload (profiles/r01_mala_c2_final_ncu.txt)
-NCU_DRAM_BYTES_PER_LAUNCH = 7.124224e6 + 4.224889e9
-NCU_WARP_INSTR_PER_CHAIN_STEP = 534.0
 WORKLOAD = "C2: 128-D AR(1) Gaussian (rho=0.9), 8192 chains/GPU, MALA step_size=0.1, 1000 local steps per call"
+METRIC = "chain-steps/s (MALA)"
+
+
+def make_config(world: int) -> dict:
+    """The `config` object of BOTH arms (the driver compares them key by key)."""
+    return {"workload": WORKLOAD, "n_dim": D, "n_chains_per_gpu": CHAINS_PER_GPU,
+            "n_chains_global": CHAINS_PER_GPU * world, "local_steps_per_bench_step": N_LOCAL_STEPS,
+            "parallelism": f"chains sharded x{world}, no collectives on the local-step path",
+            "l2": "outputs (4.26 GB per step) >> 126 MB L2, no flush needed"}
 
 
 def measured_peak():
@@ -49,6 +59,16 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_constants() -> dict:
+    """Numbers that only a profiler can give (DRAM bytes, executed instructions), read from the committed summary of
+    the ncu capture -- NOT measured in this run; every use carries its source."""
+    p = os.path.join(ROOT, "profiles", "ncu_constants.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -102,9 +122,36 @@ class ClockSampler:
                 "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def stats(ms: list) -> dict:
+    a = np.asarray(ms, dtype=np.float64)
+    return {"min": float(a.min()), "median": float(np.median(a)), "mean": float(a.mean()), "max": float(a.max()),
+            "n": int(a.size)}
+
+
+def timed_calls(fn, iters: int, warm: int) -> dict:
+    """Per-call CUDA-event times of `fn` launched back to back (one event pair per call, ONE statistic for every
+    extra: the median; min / mean / max beside it)."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    ev[0].record()
+    for i in range(iters):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return stats([ev[i].elapsed_time(ev[i + 1]) for i in range(iters)])
+
+
+def cpu_threads() -> int:
+    return int(os.cpu_count() or 1)
+
+
 def cpu_reference_rate(target_seconds: float = 12.0):
     """C restatement (oracle/c, OpenMP over chains) on a bounded sample of the workload."""
     from oracle import cref, rng, targets as otargets
+    threads = cref.set_num_threads(cpu_threads())
     key = rng.PRNGKey(1)
     n = CHAINS_PER_GPU
     x0 = rng.normal(rng.split(rng.PRNGKey(0))[1], (n, D))
@@ -117,12 +164,12 @@ def cpu_reference_rate(target_seconds: float = 12.0):
     t0 = time.perf_counter()
     cref.take_serial_steps(key, x0, "ar1_gaussian", data, "MALA", steps, step_size=STEP_SIZE, store=True)
     dt = time.perf_counter() - t0
-    return n * steps / dt, cref.num_threads(), steps, dt
+    return n * steps / dt, threads, steps, dt
 
 
 def flow_extras(dev):
-    """Short device-timed measurements of the flow kernels at the BASELINE.json shapes (C4 training batch,
-    C5 global steps); reported under "extra" next to the headline local-step metric."""
+    """Device-timed measurements of the flow kernels at the BASELINE.json shapes (C4 training batch, C5 global
+    steps); reported under "extra" next to the headline local-step metric."""
     import torch
     from flowmc_b200 import random as frandom, targets as T
     from flowmc_b200.resource.buffers import Buffer
@@ -133,46 +180,37 @@ def flow_extras(dev):
     from flowmc_b200.resource.states import State
     from flowmc_b200.strategy.take_steps import TakeGroupSteps
 
-    def timed(fn, iters=5, warm=3):
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters
-
     def useful_flops(d, L, h, K):   # transformed half of W3, conditioning half of W1
         return 2 * L * ((d // 2) * h + h * h + h * (d // 2) * (3 * K + 1))
 
+    nc = ncu_constants()
     out = {}
     # C4 flow: 32-D, 10 layers, [128,128], 8 bins
     m = MaskedCouplingRQSpline(32, 10, [128, 128], 8, frandom.PRNGKey(1), device=dev)
     n = 148 * 128 * 4
     x = frandom.normal(frandom.PRNGKey(2), (n, 32), device=dev)
-    ms = timed(lambda: m.log_prob(x))
+    st = timed_calls(lambda: m.log_prob(x), 8, 3)
+    ms = st["median"]
     fl = useful_flops(32, 10, 128, 8)
     # MMAs actually issued per sample (SURVEY 8d "dense-as-written" differs: only the transformed half of W3 is
     # multiplied, but its 4-feature chunks are padded 100 -> 112 columns and W1 sees the masked inputs as zeros)
     issued = 10 * 2 * (32 * 128 + 128 * 128 + 4 * 128 * 112) * (3 if m.desc.tc_terms == 3 else 1)
     pipe_peak = 4096.0 * 148 * 1.965e9 / 1e12   # kind::tf32 128x128x8 per 64 cycles per SM, at the maximum SM clock
     out["flow_log_prob_c4"] = {
-        "samples_per_s": n / ms * 1e3, "useful_tflops": fl * n / ms / 1e9, "path": f"tcgen05 {m.desc.tc_terms}xTF32"
-        if m.desc.tc_terms else "fp32 CUDA cores",
+        "samples_per_s": n / ms * 1e3, "ms_per_call": st, "useful_tflops": fl * n / ms / 1e9,
+        "path": f"tcgen05 {m.desc.tc_terms}xTF32" if m.desc.tc_terms else "fp32 CUDA cores",
         "issued_tflops": issued * n / ms / 1e9,
         "tensor_pipe_frac_from_rate": issued * n / ms / 1e9 / pipe_peak,
-        "tensor_pipe_active_ncu": 0.4758,
+        "tensor_pipe_active_ncu": nc.get("flow_tc_log_prob_c4", {"note": "no committed capture"}),
         "note": "issued = 3 TF32 terms x the padded GEMM shapes; pipe peak = 4096 flop/clk/SM x 148 SMs x 1.965 GHz = "
-                "1191 TFLOP/s (the cuBLAS-measured bf16_tflops/2 = 850 understates the pipe); tensor_pipe_active_ncu = "
-                "sm__pipe_tensor_cycles_active of a 148-tile launch, profiles/r01_flow_tc_c4_logprob_v2_ncu.txt"}
+                "1191 TFLOP/s (nominal; tensor_pipe_frac_from_rate is computed from THIS run's rate, "
+                "tensor_pipe_active_ncu is copied from the committed ncu summary it names, not measured in this run)"}
     opt = Optimizer(m, 1e-3)
     bs = 16384
     idx = torch.arange(bs, dtype=torch.int32, device=dev)
-    ms = timed(lambda: m.train_step(x, opt.optim, opt.optim_state, idx))
-    out["flow_train_c4"] = {"samples_per_s": bs / ms * 1e3, "batch": bs, "ms_per_step": ms,
+    st = timed_calls(lambda: m.train_step(x, opt.optim, opt.optim_state, idx), 8, 3)
+    ms = st["median"]
+    out["flow_train_c4"] = {"samples_per_s": bs / ms * 1e3, "batch": bs, "ms_per_step": st,
                             "useful_tflops": 3 * fl * bs / ms / 1e9,
                             "note": "training forward (tcgen05, leaves spline parameters + packed activation images) + "
                                     "hand-written backward (tcgen05 dgrad/wgrad, in-kernel deterministic reduction) + "
@@ -192,8 +230,9 @@ def flow_extras(dev):
     def run():
         strat.set_current_position(0)
         strat(frandom.PRNGKey(9), res, x0, None)
-    ms = timed(run)
-    out["nf_global_steps_c5"] = {"chain_steps_per_s": n_chains * n_steps / ms * 1e3, "ms_per_call": ms,
+    st = timed_calls(run, 5, 2)
+    ms = st["median"]
+    out["nf_global_steps_c5"] = {"chain_steps_per_s": n_chains * n_steps / ms * 1e3, "ms_per_call": st,
                                  "useful_tflops": 2 * useful_flops(d, 8, 128, 8) * n_chains * n_steps / ms / 1e9,
                                  "note": "65536 chains x 10 NFProposal steps: flow inverse + forward, target, accept scan"}
     return out
@@ -201,8 +240,7 @@ def flow_extras(dev):
 
 def local_extras(dev):
     """Device-timed local-step calls of the other BASELINE.json local configs (C3 HMC, the local phase of C5); reported
-    under "extra" next to the headline C2 metric."""
-    import torch
+    under "extra" next to the headline C2 metric, same statistic (median of back-to-back calls)."""
     from flowmc_b200 import random as frandom, targets as T
     from flowmc_b200.resource.buffers import Buffer
     from flowmc_b200.resource.kernel.HMC import HMC
@@ -217,24 +255,20 @@ def local_extras(dev):
                "k": kernel, "logpdf": LogPDF(target, n_dims=d)}
         strat = TakeSerialSteps("logpdf", "k", "s", ["p", "l", "a"], steps)
         x0 = frandom.normal(frandom.split(frandom.PRNGKey(0))[1], (n, d), device=dev)
-        best = float("inf")
-        for i in range(4):
+
+        def call():
             strat.set_current_position(0)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
             strat(frandom.PRNGKey(1), res, x0, None)
-            e1.record()
-            torch.cuda.synchronize()
-            if i:
-                best = min(best, e0.elapsed_time(e1))
+        st = timed_calls(call, 5, 2)
         acc = float(res["a"].data.mean())
+        plan = local_plan(kernel, res["logpdf"], n, d, steps, dev)
         del res
-        return n * steps / best * 1e3, best, acc
+        return n * steps / st["median"] * 1e3, st, acc, plan
 
     out = {}
     m = np.linspace(0.5, 2.0, 64).astype(np.float32)
-    rate, ms, acc = run(HMC(np.diag(m), 0.01, 10), T.rosenbrock(), 32768, 64, 200)
-    out["hmc_c3"] = {"chain_steps_per_s": rate, "ms_per_call": ms, "acceptance_rate": acc,
+    rate, st, acc, plan = run(HMC(np.diag(m), 0.01, 10), T.rosenbrock(), 32768, 64, 200)
+    out["hmc_c3"] = {"chain_steps_per_s": rate, "ms_per_call": st, "acceptance_rate": acc, "launch_plan": plan,
                      "workload": "C3: 64-D Rosenbrock, 32768 chains, HMC step 0.01, 10 leapfrog steps, diagonal mass, "
                                  "200 steps per call",
                      "hbm_frac": rate * 4 * (64 + 2) / 1e9 / measured_peak()[0],
@@ -242,45 +276,104 @@ def local_extras(dev):
     mu = np.zeros((8, 64), np.float32)
     for i in range(8):
         mu[i, i] = 3.0 if i % 2 == 0 else -3.0
-    rate, ms, acc = run(MALA(0.1), T.gaussian_mixture(mu, 1.0), 65536, 64, 50)
-    out["mala_c5_local"] = {"chain_steps_per_s": rate, "ms_per_call": ms, "acceptance_rate": acc,
+    rate, st, acc, plan = run(MALA(0.1), T.gaussian_mixture(mu, 1.0), 65536, 64, 50)
+    out["mala_c5_local"] = {"chain_steps_per_s": rate, "ms_per_call": st, "acceptance_rate": acc, "launch_plan": plan,
                             "workload": "C5 local phase: 64-D 8-component mixture, 65536 chains, MALA 0.1, 50 steps per call",
                             "hbm_frac": rate * 4 * (64 + 2) / 1e9 / measured_peak()[0]}
     return out
+
+
+def local_plan(kernel, logpdf, n, d, n_steps, dev) -> dict:
+    """What flowmc_local_steps decides for this call: lane layout, resident slots, time slicing, launches."""
+    import ctypes as C
+    import torch
+    from flowmc_b200._lib import check, lib
+    p, keep = kernel._local_params(d, dev)
+    ws = torch.empty(max(256, int(lib.flowmc_local_steps_workspace_bytes(n, d, p.layout_hint))), dtype=torch.uint8,
+                     device=dev)
+    p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    out = (C.c_int * 12)()
+    with torch.cuda.device(dev):
+        check(lib.flowmc_local_steps_plan(kernel.KIND, logpdf.target.target_id, n, d, n_steps, C.byref(p), out))
+    names = ["layout", "lanes_per_chain", "dims_per_lane", "store_vec", "chain_groups", "resident_cta_slots",
+             "ctas_per_sm", "static_smem_per_cta", "n_seg", "seg_len", "n_launches", "ctas_per_launch"]
+    return dict(zip(names, [int(v) for v in out]))
+
+
+def flow_train_dp(dev, rank, world, iters=20, warm=5):
+    """C4 (BASELINE.json configs[3]): one NFModel.train_step on a GLOBAL batch of 16384 rows, data-parallel over the
+    `world` ranks (each rank takes 16384 / world rows; flat gradient + loss all-reduced over NCCL; identical fused
+    clip/AdamW on every rank).  Collective: every rank calls it.  Device time, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from flowmc_b200 import random as frandom
+    from flowmc_b200.parallel import ChainShard
+    from flowmc_b200.resource.model.nf_model.rqSpline import MaskedCouplingRQSpline
+    from flowmc_b200.resource.optimizer import Optimizer
+    m = MaskedCouplingRQSpline(32, 10, [128, 128], 8, frandom.PRNGKey(1), device=dev)
+    if world > 1:
+        sh = ChainShard(world, rank, world)
+        m.dp = (rank, world, sh.all_reduce, sh.broadcast)
+    opt = Optimizer(m, 1e-3)
+    bs = 16384
+    x = frandom.normal(frandom.PRNGKey(2), (bs * 4, 32), device=dev)
+    idx = torch.arange(bs, dtype=torch.int32, device=dev)
+    from flowmc_b200.resource.model.nf_model.base import _TrainScratch
+    sc = _TrainScratch(m, 0, bs)
+    for _ in range(warm):
+        m.train_step(x, opt.optim, opt.optim_state, idx, sc)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        m.train_step(x, opt.optim, opt.optim_state, idx, sc)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"workload": "C4: flow 32-D, 10 layers, [128,128], 8 bins; train_step on a global batch of 16384 rows "
+                        f"split over {world} GPU(s)", "n_gpus": world, "ms_per_step": ms,
+            "samples_per_s": bs / ms * 1e3, "grad_allreduce_bytes": int(m.params.numel()) * 4 if world > 1 else 0,
+            "timing": f"{iters} back-to-back steps, CUDA events, max over ranks"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     from oracle import cref, rng, targets as otargets
+    threads = cref.set_num_threads(cpu_threads())     # torchrun exports OMP_NUM_THREADS=1
     key = rng.PRNGKey(1)
     n = CHAINS_PER_GPU
     x0 = rng.normal(rng.split(rng.PRNGKey(0))[1], (n, D))
     data = otargets.AR1Gaussian.pack(D, RHO)
-    cref.take_serial_steps(key, x0, "ar1_gaussian", data, "MALA", 1, step_size=STEP_SIZE, store=False)
-    t0 = time.perf_counter()
     cref.take_serial_steps(key, x0, "ar1_gaussian", data, "MALA", 2, step_size=STEP_SIZE, store=False)
-    per = (time.perf_counter() - t0) / 2
-    total_budget = 120.0  # seconds for the whole --steps/--warmup run
-    sub_steps = int(max(1, min(N_LOCAL_STEPS, total_budget / max(1, args.steps + args.warmup) / max(per, 1e-6))))
     for _ in range(args.warmup):
-        cref.take_serial_steps(key, x0, "ar1_gaussian", data, "MALA", sub_steps, step_size=STEP_SIZE)
+        cref.take_serial_steps(key, x0, "ar1_gaussian", data, "MALA", N_LOCAL_STEPS, step_size=STEP_SIZE)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cref.take_serial_steps(key, x0, "ar1_gaussian", data, "MALA", sub_steps, step_size=STEP_SIZE)
+        cref.take_serial_steps(key, x0, "ar1_gaussian", data, "MALA", N_LOCAL_STEPS, step_size=STEP_SIZE)
     dt = time.perf_counter() - t0
-    rate = n * sub_steps * args.steps / dt
-    sample = f"{n} chains x {sub_steps} MALA steps per bench step (of {N_LOCAL_STEPS}), samples stored to host memory"
+    rate = n * N_LOCAL_STEPS * args.steps / dt
+    sample = (f"{n} chains x {N_LOCAL_STEPS} MALA steps per bench step (the full per-GPU workload"
+              + (f"; 1/{world} of the {n * world} global chains -- chain-steps/s does not depend on the chain count"
+                 if world > 1 else "") + "), samples stored to host memory")
     line = {
-        "impl": "reference", "metric": "chain-steps/s (MALA)", "value": rate, "unit": "chain-steps/s",
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "chain-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_dim": D, "n_chains": n, "local_steps_per_bench_step": sub_steps},
-        "cpu_baseline": {"value": rate, "unit": "chain-steps/s", "cores": cref.num_threads(), "kind": "port",
+        "config": make_config(world),
+        "cpu_baseline": {"value": rate, "unit": "chain-steps/s", "cores": threads, "kind": "port",
                          "sample": sample,
-                         "note": "C restatement of flowMC's MALA path (oracle/c, OpenMP over chains); the "
-                                 "reference's own JAX CPU path cannot run here (jax not installable)"},
+                         "note": "C restatement of flowMC's MALA path (oracle/c, OpenMP over chains, pinned to the numpy "
+                                 "oracle by tests/test_oracle_c.py); the reference's own JAX CPU path cannot run here "
+                                 "(jax not installable)"},
         "e2e": {"value": rate, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -325,6 +418,7 @@ def run_ours(args):
     x0 = frandom.normal(x0_all_key, (n_global, D), device=dev)[rank * n:(rank + 1) * n].contiguous()
     x0_host = x0.cpu().pin_memory()
     key = frandom.PRNGKey(1)
+    plan = local_plan(resources["kernel"], resources["logpdf"], n, D, N_LOCAL_STEPS, dev)
 
     def step_device(k):
         strat.set_current_position(0)
@@ -336,7 +430,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput (`value`) -----------------------------------------------
+    # ---- device-resident throughput (`value`): K calls back to back ------------------------------------------
     k = key
     for _ in range(args.warmup):
         k, _ = step_device(k)
@@ -356,6 +450,16 @@ def run_ours(args):
     launches = lib.flowmc_launch_count() - launches0
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    # ... and the same calls with a device synchronisation after each (launch-to-launch effects show as a difference)
+    sync_ms = []
+    for i in range(min(args.steps, 10)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        k, last = step_device(k)
+        e1.record()
+        torch.cuda.synchronize()
+        sync_ms.append(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     acc_rate = float(resources["acceptance"].data.mean())
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -399,32 +503,52 @@ def run_ours(args):
         res_e2e[full] = chain_steps_per_step * e2e_steps / float(dt.item())
     h2d = x0_host.numel() * 4
     d2h_full = (out_pos.numel() + out_lp.numel() + out_acc.numel() + out_last.numel()) * 4
+    del out_pos, out_lp, out_acc
+    del resources["positions"], resources["log_prob"], resources["acceptance"]
+    torch.cuda.empty_cache()
+
+    # ---- the communicating paths on the same ranks (collective: every rank takes part) -------------------------
+    # FLOWMC_BENCH_EXTRAS=0 skips everything below the headline (used for the ncu launch list of the timed step itself)
+    extras_on = os.environ.get("FLOWMC_BENCH_EXTRAS", "1") != "0"
+    scaled = {"skipped": "FLOWMC_BENCH_EXTRAS=0"}
+    if extras_on:
+        scaled = {}
+        try:
+            scaled["flow_train_c4_dp"] = flow_train_dp(dev, rank, world)
+        except Exception as ex:  # the headline line must still be printed
+            scaled["flow_train_c4_dp"] = {"error": repr(ex)}
+        try:
+            from scripts.bench_sampler import run_sampler
+            scaled["sampler_c5"] = run_sampler(dev, rank, world)
+        except Exception as ex:
+            scaled["sampler_c5"] = {"error": repr(ex)}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # FLOWMC_BENCH_EXTRAS=0 skips the flow add-ons (used for the ncu launch list of the timed step itself)
-    extras = {"skipped": "FLOWMC_BENCH_EXTRAS=0"}
-    if os.environ.get("FLOWMC_BENCH_EXTRAS", "1") != "0":
+    extras = {"skipped": "FLOWMC_BENCH_EXTRAS=0" if not extras_on else "single-GPU kernel extras are reported at N=1"}
+    if extras_on and world == 1:
         try:
             extras = flow_extras(dev)
             extras.update(local_extras(dev))
-        except Exception as ex:  # the headline line must still be printed
+        except Exception as ex:
             extras = {"error": repr(ex)}
     peak, peak_src = measured_peak()
-    avg_kernel_ms = float(np.mean(kernel_ms))
+    kst = stats(kernel_ms)
+    avg_kernel_ms = kst["mean"]
     achieved = n * N_LOCAL_STEPS * BYTES_PER_CHAIN_STEP / (avg_kernel_ms * 1e-3) / 1e9
-    cpu_rate, cpu_threads, cpu_steps, cpu_dt = cpu_reference_rate()
+    nc = ncu_constants().get("local_steps_c2", {})
+    traffic = nc.get("dram_bytes_per_step")
+    instr = nc.get("warp_instr_per_chain_step")
+    sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
     line = {
-        "metric": "chain-steps/s (MALA)", "value": value, "unit": "chain-steps/s", "n_gpus": world,
+        "metric": METRIC, "value": value, "unit": "chain-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_dim": D, "n_chains_per_gpu": n, "n_chains_global": n_global,
-                   "local_steps_per_bench_step": N_LOCAL_STEPS, "parallelism": f"chains sharded x{world}, no collectives",
-                   "l2": "outputs (4.26 GB per step) >> 126 MB L2, no flush needed",
-                   "acceptance_rate": acc_rate},
+        "config": make_config(world),
+        "acceptance_rate": acc_rate,
         "e2e": {"value": res_e2e[True], "unit": "chain-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h_full,
                 "note": "TakeSerialSteps call with pinned-host initial positions in and ALL sample buffers "
@@ -435,27 +559,37 @@ def run_ours(args):
             "note": "same call, buffers stay on the device as in the reference (jax arrays); only the "
                     "strategy's return value (positions[:, -1]) is read back"},
         "gpu_launches": int(launches),
+        "launch_plan": plan,
+        "per_step_ms": {"back_to_back": kst, "sync_per_step": stats(sync_ms),
+                        "note": "CUDA-event time of each of the K timed steps (one TakeSerialSteps call = "
+                                f"{plan['n_launches']} launches of local_steps_kernel); `value` uses the back-to-back total"},
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH * (n / CHAINS_PER_GPU), "peak_source": peak_src,
-                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one launch "
-                                       "(profiles/r01_mala_c2_final_ncu.txt): 7.1 MB read + 4224.9 MB written = 0.993 x "
-                                       "the algorithmic bytes",
-                     "kernel": "flowmc::local_steps_kernel<AR1Gaussian, MALA, Layout<...>>",
+                     "traffic": traffic, "peak_source": peak_src,
+                     "traffic_source": nc.get("source", "no committed ncu capture") + " (ncu --set full, dram__bytes_read.sum "
+                                       "+ dram__bytes_write.sum summed over the launches of one step; NOT measured in this run)",
+                     "kernel": "flowmc::local_steps_kernel<AR1Gaussian, MALA, Layout<16,8,4>>",
                      "algorithmic_bytes_per_launch": n * N_LOCAL_STEPS * BYTES_PER_CHAIN_STEP,
+                     "launches_per_step": plan["n_launches"],
                      "avg_launch_ms": avg_kernel_ms,
+                     "avg_launch_ms_note": "mean over the K timed steps of the device time of one step (all of its "
+                                           "local_steps_kernel launches); algorithmic bytes are per step likewise",
                      "issue_slots": {
-                         "warp_instructions_per_chain_step": NCU_WARP_INSTR_PER_CHAIN_STEP,
-                         "achieved_frac": (n * N_LOCAL_STEPS / (avg_kernel_ms * 1e-3)) * NCU_WARP_INSTR_PER_CHAIN_STEP /
-                                          (148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6),
-                         "note": "executed warp-instructions (ncu smsp__inst_executed.sum / chain-steps) x measured "
-                                 "chain-steps/s over 148 SMs x 4 schedulers x the SM clock sampled during the run"},
+                         "warp_instructions_per_chain_step": instr,
+                         "achieved_frac": ((n * N_LOCAL_STEPS / (avg_kernel_ms * 1e-3)) * instr / (148 * 4 * sm_hz))
+                         if instr else None,
+                         "source": nc.get("source", "no committed ncu capture") + " (smsp__inst_executed.sum / chain-steps; "
+                                   "NOT measured in this run) x this run's chain-steps/s over 148 SMs x 4 schedulers x the "
+                                   "SM clock sampled during the run"},
                      "note": "bit-exact threefry2x32 (d+5 blocks per chain-step) + XLA's erf_inv make this kernel "
                              "instruction-issue bound, not HBM bound: see issue_slots and DESIGN.md 4.1"},
-        "cpu_baseline": {"value": cpu_rate, "unit": "chain-steps/s", "cores": cpu_threads, "kind": "port",
-                         "sample": f"{n} chains x {cpu_steps} MALA steps ({cpu_dt:.1f} s), same target and seeds"},
+        "scaled": scaled,
         "extra": extras,
     }
+    if world == 1:
+        cpu_rate, cpu_thr, cpu_steps, cpu_dt = cpu_reference_rate()
+        line["cpu_baseline"] = {"value": cpu_rate, "unit": "chain-steps/s", "cores": cpu_thr, "kind": "port",
+                                "sample": f"{n} chains x {cpu_steps} MALA steps ({cpu_dt:.1f} s), same target and seeds"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

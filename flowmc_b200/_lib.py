@@ -30,6 +30,8 @@ class LocalParams(C.Structure):
         ("chain_keys", C.c_void_p),
         ("beta", C.c_void_p),
         ("prior", C.c_void_p),
+        ("force_n_seg", C.c_int),
+        ("slots_override", C.c_int),
     ]
 
 
@@ -81,6 +83,7 @@ def _load() -> C.CDLL:
         "flowmc_random_normal": (i32, [u32p, i64, vp, vp]),
         "flowmc_local_steps": (i32, [i32, i32, vp, u32p, vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, i64, i64,
                                      C.POINTER(LocalParams), u32p, vp, vp]),
+        "flowmc_local_steps_plan": (i32, [i32, i32, i64, i32, i32, C.POINTER(LocalParams), C.POINTER(C.c_int)]),
         "flowmc_adam_optimize": (i32, [i32, vp, u32p, vp, i64, i32, i32, f32, f32, vp, vp, vp, i64, i64, u32p, vp, vp,
                                        vp]),
         "flowmc_pt_exchange": (i32, [u32p, i64, i64, i64, i32, i32, vp, vp, vp, vp, vp]),

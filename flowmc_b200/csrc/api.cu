@@ -283,7 +283,38 @@ int flowmc_local_steps(int kind, int target_id, const float* target_data, const 
   a.chain_keys = params->chain_keys;
   a.beta = params->beta;
   a.prior = params->prior;
+  a.force_n_seg = params->force_n_seg;
+  a.slots_override = params->slots_override;
+  a.plan_out = nullptr;
   return vt.local_steps(kind, &a, (cudaStream_t)stream);
+}
+
+int flowmc_local_steps_plan(int kind, int target_id, int64_t n_chains, int d, int n_steps,
+                            const FlowmcLocalParams* params, int plan[12]) {
+  FlowmcTargetVTable vt;
+  if (int rc = flowmc_get_target(target_id, &vt)) return rc;
+  if (!params || !plan || n_chains <= 0 || d <= 0 || n_steps <= 0)
+    return fail(FLOWMC_ERR_INVALID, "local_steps_plan: bad arguments");
+  flowmc::LocalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_chains = n_chains;
+  a.d = d;
+  a.n_steps = n_steps;
+  a.thinning = 1;
+  a.layout_hint = params->layout_hint;
+  a.step_keys = params->step_keys;
+  a.workspace = params->workspace;
+  a.workspace_bytes = params->workspace_bytes;
+  a.force_n_seg = params->force_n_seg;
+  a.slots_override = params->slots_override;
+  flowmc::LocalPlan p;
+  memset(&p, 0, sizeof(p));
+  a.plan_out = &p;
+  if (int rc = vt.local_steps(kind, &a, nullptr)) return rc;
+  const int v[12] = {p.layout, p.G, p.DPL, p.VEC, p.n_groups, p.slots, p.ctas_per_sm, p.smem_per_cta,
+                     p.n_seg, p.seg_len, p.n_rounds, p.round_size};
+  memcpy(plan, v, sizeof(v));
+  return FLOWMC_OK;
 }
 
 int flowmc_adam_optimize(int target_id, const float* target_data, const uint32_t key[2], const float* x0,

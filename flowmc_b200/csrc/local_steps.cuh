@@ -24,11 +24,15 @@
 // one step per lane and parked in shared memory.  Bits are identical to jax.random's.
 //
 // Time slicing.  All chains cost the same, so with more warps than resident slots a plain grid
-// runs ceil(waves) full-length waves.  Instead the step range is cut into S segments; CTA
-// (segment s, group g) -- numbered by an atomic ticket so that predecessors always start first --
-// runs steps [s*Ls, (s+1)*Ls) of group g and hands the chain state (position, cached gradient,
-// log-prob, chain key) to CTA (s+1, g) through a small global workspace guarded by a per-group
-// flag.  The host picks S to minimise ceil(groups*S/slots)*Ls; S = 1 when everything is resident.
+// runs ceil(waves) full-length waves.  Instead the step range is cut into S segments and the
+// (segment, group) work items, numbered item = segment * n_groups + group, run as ROUNDS: launch r
+// holds the items [r * R, (r + 1) * R) with R = min(slots, n_groups) CTAs, i.e. exactly one resident
+// wave.  Item (s, g) runs steps [s*Ls, (s+1)*Ls) of group g and leaves the chain state (position,
+// cached gradient, log-prob, chain key) in a small global workspace for item (s+1, g), which lies
+// n_groups >= R items later and therefore always in a LATER launch on the same stream: the
+// kernel boundary is the only synchronisation (no flags, no spinning, no fences), so the schedule
+// and its duration are deterministic.  The host picks S to minimise ceil(groups*S/R) * (Ls + c);
+// S = 1 (one launch) when everything is resident.
 //
 // The gradient of the current point is carried across steps (the reference recomputes it every
 // step, MALA.py:59 -- same value, half the work).
@@ -212,10 +216,10 @@ struct Slice {       // time-slicing parameters (host-computed)
   int n_seg;         // number of segments S (1 = no slicing)
   int seg_len;       // steps per segment
   int n_groups;      // ceil(n_chains / CPW)
-  int* ticket;       // workspace: 1 int, zeroed before launch
-  int* flags;        // workspace: n_groups ints, zeroed before launch (segments completed per group)
-  float* state;      // workspace: n_groups * NSTATE * 32 floats
+  int item_base;     // first (segment, group) work item of this launch
+  float* state;      // workspace: n_groups * NSTATE * 32 floats (hand-off between segments)
 };
+
 
 template <class T, int KIND, class L, int MINB>
 __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a, const Slice sl) {
@@ -226,16 +230,10 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
   const int lg = lane % G;
   const int cw = lane / G;
 
-  // which (segment, group) this CTA runs: tickets are issued in start order, so the CTA that owns
-  // (seg-1, grp) has always started before this one
-  int seg = 0, grp = blockIdx.x;
-  if (sl.n_seg > 1) {
-    int tk = 0;
-    if (lane == 0) tk = atomicAdd(sl.ticket, 1);
-    tk = __shfl_sync(0xffffffffu, tk, 0);
-    seg = tk / sl.n_groups;
-    grp = tk - seg * sl.n_groups;
-  }
+  // which (segment, group) work item this CTA runs; item (seg-1, grp) ran in an earlier launch
+  const int item = sl.item_base + (int)blockIdx.x;
+  const int seg = item / sl.n_groups;
+  const int grp = item - seg * sl.n_groups;
   const int t_begin = seg * sl.seg_len;
   const int t_end = min(a.n_steps, t_begin + sl.seg_len);
 
@@ -283,15 +281,11 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
     // logpdf(initial_position) seeds the scan carry (take_steps.py:177); MALA/HMC cache the gradient
     if (TEMPERED) lp = eval_grad(x, g);
     else lp = eval_target<T, L, KIND != KIND_GRW>(tc, x, g, xrow, scratch, a.data, d, lg);
-    if (a.lp0 != nullptr) lp = a.lp0[chain];  // ProposalBase.kernel(): caller-supplied log_prob
+    // ProposalBase.kernel(): HMC and GRW use the caller-supplied log_prob (HMC.py:137,
+    // Gaussian_random_walk.py:56); MALA ignores it and re-evaluates logpdf(position) (MALA.py:59,75,87)
+    if (a.lp0 != nullptr && !IS_MALA) lp = a.lp0[chain];
   } else {
-    // wait for the previous time slice of this group, then pick up its state
-    if (lane == 0) {
-      const volatile int* f = sl.flags + grp;
-      while (*f < seg) __nanosleep(200);
-    }
-    __syncwarp();
-    __threadfence();
+    // pick up the state the previous time slice of this group left (an earlier launch on this stream)
     const float* st = sl.state + ((int64_t)grp * NS) * 32 + lane;
 #pragma unroll
     for (int k = 0; k < DPL; ++k) {
@@ -510,9 +504,6 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
     __stcg(st + (2 * DPL) * 32, lp);
     __stcg(st + (2 * DPL + 1) * 32, __uint_as_float(kc.k0));
     __stcg(st + (2 * DPL + 2) * 32, __uint_as_float(kc.k1));
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) atomicExch(sl.flags + grp, seg + 1);
   }
 }
 
@@ -607,8 +598,39 @@ __host__ inline int64_t local_workspace_bytes(int64_t n_chains, int d, int hint)
   const LayoutInfo L = layout_info(li);
   const int64_t cpw = 32 / L.G;
   const int64_t n_groups = (n_chains + cpw - 1) / cpw;
-  const int64_t head = 256 + ((n_groups * 4 + 255) / 256) * 256;
-  return head + n_groups * (2 * L.DPL + 3) * 32 * 4;
+  return n_groups * (2 * L.DPL + 3) * 32 * 4;
+}
+
+// Resident CTA slots of one kernel instantiation on the current device.  The shared-memory carve-out is pinned to what
+// MINB CTAs per SM need (the driver's default heuristic may pick a smaller one and halve the occupancy), then the
+// occupancy is queried once per device.
+template <class K>
+inline void local_slots(K kern, int minb, int* slots_out, int* per_sm_out, int* smem_out) {
+  constexpr int kMaxDev = 64;
+  static int slots[kMaxDev] = {0}, per_sm_c[kMaxDev] = {0}, smem_c[kMaxDev] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int di = (dev >= 0 && dev < kMaxDev) ? dev : 0;
+  if (slots[di] == 0) {
+    int sms = 0, per_sm = 0, smem_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kern);
+    const int64_t need = (int64_t)minb * ((int64_t)fa.sharedSizeBytes + 1024);  // + the per-CTA reservation
+    int pct = smem_sm > 0 ? (int)((need * 100 + smem_sm - 1) / smem_sm) + 1 : 50;
+    if (pct > 100) pct = 100;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, 0);
+    if (per_sm <= 0) per_sm = 1;
+    per_sm_c[di] = per_sm;
+    smem_c[di] = (int)fa.sharedSizeBytes;
+    slots[di] = sms * per_sm;
+    cudaGetLastError();
+  }
+  *slots_out = slots[di];
+  *per_sm_out = per_sm_c[di];
+  *smem_out = smem_c[di];
 }
 
 template <class T, int KIND, int G, int DPL, int VEC, int MINB, bool PAD = true>
@@ -616,49 +638,58 @@ inline int launch_local_one(const LocalArgs* a, cudaStream_t stream) {
   using L = Layout<G, DPL, VEC, PAD>;
   auto kern = local_steps_kernel<T, KIND, L, MINB>;
   const int64_t n_groups = (a->n_chains + L::CPW - 1) / L::CPW;
-  Slice sl{1, a->n_steps, (int)n_groups, nullptr, nullptr, nullptr};
+  Slice sl{1, a->n_steps, (int)n_groups, 0, nullptr};
 
-  // resident slots for this kernel (cached per instantiation)
-  static int slots = 0;
-  if (slots == 0) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, 0);
-    slots = sms * (per_sm > 0 ? per_sm : 1);
-  }
-  const int64_t head = 256 + ((n_groups * 4 + 255) / 256) * 256;
-  const int64_t need = head + n_groups * L::NSTATE * 32 * 4;
-  const int max_seg = a->n_steps / kChunk;  // keep segments >= one key-schedule chunk
-  if (n_groups > slots && max_seg >= 2 && a->workspace != nullptr && a->workspace_bytes >= need &&
-      a->step_keys == nullptr) {
-    // choose S minimising (rounds of resident CTAs) x (segment length)
-    int64_t best_cost = ((n_groups + slots - 1) / slots) * (int64_t)a->n_steps;
-    int best_s = 1, best_len = a->n_steps;
-    for (int s = 2; s <= (max_seg < 48 ? max_seg : 48); ++s) {
-      const int len = (a->n_steps + s - 1) / s;
-      const int s_eff = (a->n_steps + len - 1) / len;
-      const int64_t rounds = (n_groups * s_eff + slots - 1) / slots;
-      const int64_t cost = rounds * (len + 2);  // +2: per-slice hand-off overhead in step units
-      if (cost < best_cost) {
-        best_cost = cost;
-        best_s = s_eff;
-        best_len = len;
+  int slots = 0, per_sm = 0, smem = 0;
+  local_slots(kern, MINB, &slots, &per_sm, &smem);
+  if (a->slots_override > 0) slots = a->slots_override;  // tests: force rounds with small grids
+  const int64_t need = n_groups * L::NSTATE * 32 * 4;
+  const bool can_slice = a->workspace != nullptr && a->workspace_bytes >= need && a->step_keys == nullptr;
+  if (a->force_n_seg > 1) {
+    if (!can_slice) {
+      flowmc_set_error("local_steps: force_n_seg needs a workspace (flowmc_local_steps_workspace_bytes) and no step_keys");
+      return -1;
+    }
+    const int s = a->force_n_seg < a->n_steps ? a->force_n_seg : a->n_steps;
+    sl.seg_len = (a->n_steps + s - 1) / s;
+    sl.n_seg = (a->n_steps + sl.seg_len - 1) / sl.seg_len;
+  } else if (a->force_n_seg == 0) {
+    const int max_seg = a->n_steps / kChunk;  // keep segments >= one key-schedule chunk
+    if (n_groups > slots && max_seg >= 2 && can_slice) {
+      // choose S minimising (rounds of resident CTAs) x (segment length)
+      int64_t best_cost = ((n_groups + slots - 1) / slots) * (int64_t)a->n_steps;
+      for (int s = 2; s <= (max_seg < 48 ? max_seg : 48); ++s) {
+        const int len = (a->n_steps + s - 1) / s;
+        const int s_eff = (a->n_steps + len - 1) / len;
+        const int64_t rounds = (n_groups * s_eff + slots - 1) / slots;
+        const int64_t cost = rounds * (len + 2);  // +2: per-round launch + hand-off overhead in step units
+        if (cost < best_cost) {
+          best_cost = cost;
+          sl.n_seg = s_eff;
+          sl.seg_len = len;
+        }
       }
     }
-    if (best_s > 1) {
-      char* ws = static_cast<char*>(a->workspace);
-      sl.n_seg = best_s;
-      sl.seg_len = best_len;
-      sl.ticket = reinterpret_cast<int*>(ws);
-      sl.flags = reinterpret_cast<int*>(ws + 256);
-      sl.state = reinterpret_cast<float*>(ws + head);
-      cudaMemsetAsync(ws, 0, (size_t)head, stream);
-    }
+  }  // force_n_seg < 0: never slice
+  if (sl.n_seg > 1) sl.state = reinterpret_cast<float*>(a->workspace);
+  // a round = one resident wave; item (s, g) depends on item (s-1, g) = n_groups items earlier, which is in an earlier
+  // round as long as a round holds at most n_groups items
+  const int64_t n_items = n_groups * sl.n_seg;
+  const int64_t round = sl.n_seg > 1 ? (slots < n_groups ? slots : n_groups) : n_items;
+  if (a->plan_out != nullptr) {
+    LocalPlan* p = a->plan_out;
+    p->G = G; p->DPL = DPL; p->VEC = VEC;
+    p->n_groups = (int)n_groups; p->slots = slots; p->ctas_per_sm = per_sm; p->smem_per_cta = smem;
+    p->n_seg = sl.n_seg; p->seg_len = sl.seg_len;
+    p->n_rounds = (int)((n_items + round - 1) / round); p->round_size = (int)round;
+    return 0;  // plan only
   }
-  const int64_t nblk = n_groups * sl.n_seg;
-  kern<<<(unsigned)nblk, 32, 0, stream>>>(*a, sl);
-  flowmc_count_launch();
+  for (int64_t base = 0; base < n_items; base += round) {
+    sl.item_base = (int)base;
+    const int64_t nblk = (n_items - base < round) ? n_items - base : round;
+    kern<<<(unsigned)nblk, 32, 0, stream>>>(*a, sl);
+    flowmc_count_launch();
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     flowmc_set_error(cudaGetErrorString(e));
@@ -677,6 +708,7 @@ inline int launch_local_v4(const LocalArgs* a, cudaStream_t stream) {
 template <class T, int KIND>
 inline int launch_local_kind(const LocalArgs* a, cudaStream_t stream) {
   const int li = pick_layout(a->d, a->layout_hint);
+  if (a->plan_out != nullptr) a->plan_out->layout = li;
   switch (li) {
     case 0: return launch_local_one<T, KIND, 1, 8, 1, 16>(a, stream);
     case 1: return launch_local_one<T, KIND, 4, 8, 1, 16>(a, stream);

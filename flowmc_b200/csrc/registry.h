@@ -4,9 +4,16 @@
 #include <cuda_runtime.h>
 #include "rng.cuh"
 
-#define FLOWMC_TARGET_ABI 2
+#define FLOWMC_TARGET_ABI 3
 
 namespace flowmc {
+
+// what the local-steps launcher decided for a call (flowmc_local_steps_plan; bench.py and tests print / assert it)
+struct LocalPlan {
+  int layout, G, DPL, VEC;
+  int n_groups, slots, ctas_per_sm, smem_per_cta;
+  int n_seg, seg_len, n_rounds, round_size;
+};
 
 // Arguments of one persistent local-steps launch (POD, passed by value to the kernel).
 struct LocalArgs {
@@ -37,6 +44,9 @@ struct LocalArgs {
   const float* prior;         // KIND_MALA_PT: [4][d] = c, m, lo, hi of the quadratic / box log-prior (NULL = 0)
   void* workspace;            // optional: time-slicing scratch (see local_steps.cuh)
   int64_t workspace_bytes;
+  int force_n_seg;            // 0 = auto; > 1: cut the step range into this many segments; < 0: never slice
+  int slots_override;         // 0 = the device's resident CTA slots; > 0: pretend there are this many (tests)
+  LocalPlan* plan_out;        // host, optional: fill in the launch plan and return WITHOUT launching
 };
 
 // arguments of the AdamOptimization kernel (adam_opt.cuh)

@@ -5,10 +5,11 @@ The reference has no multi-device code at all; this is the
 BASELINE.json's north_star asks for:
   * chains [offset, offset + n_local) live on this rank; per-chain PRNG keys are taken from the
     GLOBAL ``split(subkey, n_chains)`` so any sharding reproduces the single-GPU chains bit for bit;
-  * TrainModel: every rank gathers the selected training rows that belong to its chains into a
-    zero-filled [n_max_examples, d] buffer and a sum-all-reduce assembles the full set on every rank
-    (an all-gather of disjoint rows); training then splits each global batch across ranks and
-    sum-all-reduces the flat gradient vector (NCCL over NVLink; gloo in the CPU tests).
+  * TrainModel: every rank gathers the selected training rows that belong to its chains into its block of a
+    [world, rows_per_rank, d] buffer and an all-gather (``all_gather_into_tensor``) gives every rank all blocks,
+    which are then put back into the order of the global ``choice`` draw; training splits each global batch
+    across ranks and sum-all-reduces the flat gradient vector + loss (NCCL over NVLink; gloo in the CPU tests);
+    ``data_mean`` / ``data_cov`` are broadcast from rank 0 so that every replica whitens identically.
 """
 from __future__ import annotations
 
@@ -26,20 +27,79 @@ class ChainShard:
         self.offset = min(self.n_chains_global, self.rank * per)
         self.n_local = min(self.n_chains_global, self.offset + per) - self.offset
 
+    def _staged(self, t: torch.Tensor) -> bool:
+        """gloo moves host memory: CUDA tensors are staged through the host (single-GPU multi-process tests)."""
+        return t.is_cuda and dist.get_backend(self.group) == "gloo"
+
     def slab(self, x: torch.Tensor) -> torch.Tensor:
         """This rank's rows of a [n_chains_global, ...] tensor."""
         return x[self.offset:self.offset + self.n_local]
 
     def all_reduce(self, t: torch.Tensor, op: str = "sum"):
         if self.world_size > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=self.group)
+            rop = dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM
+            if self._staged(t):
+                h = t.cpu()
+                dist.all_reduce(h, op=rop, group=self.group)
+                t.copy_(h)
+            else:
+                dist.all_reduce(t, op=rop, group=self.group)
         return t
+
+    def broadcast(self, t: torch.Tensor, src: int = 0):
+        if self.world_size > 1:
+            gsrc = dist.get_global_rank(self.group, src) if self.group is not None else src
+            if self._staged(t):
+                h = t.cpu()
+                dist.broadcast(h, src=gsrc, group=self.group)
+                t.copy_(h)
+            else:
+                dist.broadcast(t, src=gsrc, group=self.group)
+        return t
+
+    def all_gather_blocks(self, block: torch.Tensor) -> torch.Tensor:
+        """Every rank contributes one equally-shaped ``block``; returns [world_size, *block.shape]."""
+        if self.world_size == 1:
+            return block.unsqueeze(0)
+        src = block.cpu() if self._staged(block) else block.contiguous()
+        out = torch.empty((self.world_size * block.shape[0],) + tuple(block.shape[1:]), dtype=block.dtype,
+                          device=src.device)
+        dist.all_gather_into_tensor(out, src, group=self.group)
+        return out.to(block.device).view((self.world_size,) + tuple(block.shape))
+
+    def owner_of_chain(self, chain: torch.Tensor) -> torch.Tensor:
+        per = -(-self.n_chains_global // self.world_size)
+        return torch.div(chain, per, rounding_mode="floor")
+
+    def assemble_rows(self, idx: torch.Tensor, window: int, d: int, gather_own) -> torch.Tensor:
+        """All-gather assembly of the training set.  ``idx`` [m] is the global ``choice`` draw, known to
+        every rank (row q of the population belongs to global chain q // window).  Rows are grouped by owning rank
+        (stable), ``gather_own(my_idx, block)`` fills this rank's block with the rows of its own chains, one
+        ``all_gather_into_tensor`` moves every block to every rank, and the blocks go back into draw order."""
+        m = int(idx.numel())
+        owner = self.owner_of_chain(torch.div(idx, window, rounding_mode="floor")).to(torch.int64)
+        order = torch.argsort(owner, stable=True)
+        counts = [int(c) for c in torch.bincount(owner, minlength=self.world_size).tolist()]
+        starts = [0]
+        for c in counts:
+            starts.append(starts[-1] + c)
+        cap = max(1, max(counts))
+        mine = order[starts[self.rank]:starts[self.rank + 1]]
+        block = torch.zeros((cap, d), dtype=torch.float32, device=idx.device)
+        if mine.numel():
+            gather_own(idx[mine].contiguous(), block)
+        blocks = self.all_gather_blocks(block)                          # [world, cap, d]
+        out = torch.empty((m, d), dtype=torch.float32, device=idx.device)
+        for r in range(self.world_size):
+            if counts[r]:
+                out[order[starts[r]:starts[r + 1]]] = blocks[r, :counts[r]]
+        return out
 
     def attach(self, local_stepper, global_stepper, model_trainer, model):
         local_stepper.set_chain_shard(self.offset, self.n_chains_global)
         global_stepper.set_chain_shard(self.offset, self.n_chains_global)
-        model_trainer.set_chain_shard(self.offset, self.n_chains_global, self.all_reduce)
-        model.dp = (self.rank, self.world_size, self.all_reduce)
+        model_trainer.set_chain_shard(self.offset, self.n_chains_global, self.all_reduce, self)
+        model.dp = (self.rank, self.world_size, self.all_reduce, self.broadcast)
 
     def gather_chains(self, x: torch.Tensor) -> torch.Tensor:
         """All ranks' slabs concatenated along the chain axis (for users who want the full buffer)."""

@@ -64,6 +64,8 @@ class HMC(LocalKernel):
         p.hmc_colsum = cs.data_ptr()
         p.hmc_chol_diagonal = 1 if diag else 0
         p.layout_hint = int(self.layout_hint)
+        p.force_n_seg = int(self.force_n_seg)
+        p.slots_override = int(self.slots_override)
         return p, [Ld, cs]
 
     def print_parameters(self):

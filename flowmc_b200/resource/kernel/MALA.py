@@ -23,6 +23,8 @@ class MALA(LocalKernel):
         p = LocalParams()
         p.step_size = float(self.step_size)
         p.layout_hint = int(self.layout_hint)
+        p.force_n_seg = int(self.force_n_seg)
+        p.slots_override = int(self.slots_override)
         return p, []
 
     def print_parameters(self):

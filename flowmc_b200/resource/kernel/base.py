@@ -36,6 +36,10 @@ class LocalKernel(ProposalBase):
 
     KIND: int = -1
     layout_hint: int = 0
+    # launch-plan overrides of flowmc_local_steps (FlowmcLocalParams.force_n_seg / slots_override): results do not
+    # depend on them; tests use them to drive the time-sliced multi-launch path with small shapes
+    force_n_seg: int = 0
+    slots_override: int = 0
 
     def __init__(self):
         pass
@@ -66,7 +70,8 @@ class LocalKernel(ProposalBase):
         last = torch.empty((n, d), dtype=torch.float32, device=dev)
         params, keep = self._local_params(d, dev)
         params.step_keys = keys_d.data_ptr()
-        params.lp0 = lp_in.data_ptr()
+        params.lp0 = lp_in.data_ptr()   # used by HMC / GRW; MALA re-evaluates logpdf(position) like MALA.py:59,75
+        params.force_n_seg = 0
         pk = logpdf.target.packed_on(data, d, dev)
         dummy = np.zeros(2, np.uint32)
         out_key = np.zeros(2, np.uint32)

@@ -77,11 +77,15 @@ class NFModel(Resource):
         raise NotImplementedError
 
     # ---- training (nf_model/base.py:98-210) -----------------------------------------------------
-    # Data parallelism: ``dp = (rank, world_size, all_reduce)`` -- every rank holds the full training set
-    # and the identical permutation, takes its contiguous slice of each global batch, and the flat
-    # gradient + loss are sum-all-reduced before the (identical) optimiser step on every rank.
+    # Data parallelism: ``dp = (rank, world_size, all_reduce[, broadcast])`` -- every rank holds the full training
+    # set and the identical permutation, takes its contiguous slice of each global batch, and the flat
+    # gradient + loss are sum-all-reduced before the (identical) optimiser step on every rank.  The all-reduce
+    # result is bit-identical on every rank, so with identical initial parameters and identical whitening
+    # constants (``train`` broadcasts data_mean / data_cov from rank 0) the replicas stay in lock-step.
+    # FLOWMC_DP_MIN_ROWS (default 0 = always split): below this many rows per rank every rank takes the full
+    # batch instead and the gradient is still all-reduced (averaged), so replicas cannot drift either way.
     dp = None
-    dp_min_rows_per_rank = int(os.environ.get("FLOWMC_DP_MIN_ROWS", 64 * 128))
+    dp_min_rows_per_rank = int(os.environ.get("FLOWMC_DP_MIN_ROWS", 0))
 
     def loss_and_grad(self, x, idx=None, scratch=None, n_global=None):
         """NFModel.loss_fn (base.py:98-100): (-mean log_prob, flat gradient).  ``idx`` (int32 device
@@ -109,15 +113,17 @@ class NFModel(Resource):
         loss as a 1-element device tensor (no host synchronisation)."""
         n = int(idx.numel()) if idx is not None else int(x.shape[0])
         sc = scratch or _TrainScratch(self, 0, n)
-        if self.dp is None or n < self.dp[1] * self.dp_min_rows_per_rank:
-            # One GPU -- or a batch too small to split: a step of up to 148 128-row tiles is ONE latency-bound wave, a
-            # slice of it takes almost as long as the whole, and the gradient all-reduce adds to it (C5, batch 16384:
-            # data-parallel wins 3 % on 2 GPUs, loses 6 % on 8).  Below 64 tiles per rank every rank takes the
-            # identical full-batch step instead (the gradients are bit-reproducible, so the replicas stay in
-            # lock-step without communication).
+        if self.dp is None or self.dp[1] == 1:
             self.loss_and_grad(x, idx, sc)
+        elif n < self.dp[1] * self.dp_min_rows_per_rank:
+            # opt-in (FLOWMC_DP_MIN_ROWS): every rank takes the whole batch, scaled 1 / world, and the all-reduce
+            # averages the replicas' gradients -- the same update on every rank, bit for bit
+            all_reduce = self.dp[2]
+            self.loss_and_grad(x, idx, sc, n_global=n * self.dp[1])
+            all_reduce(sc.grad)
+            all_reduce(sc.loss)
         else:
-            rank, world, all_reduce = self.dp
+            rank, world, all_reduce = self.dp[:3]
             per = -(-n // world)
             lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
             if idx is None:
@@ -165,6 +171,11 @@ class NFModel(Resource):
         with torch.cuda.device(data.device):                      # base.py:187-188
             check(lib.flowmc_data_mean_cov(data.data_ptr(), n, d, model.data_mean.data_ptr(),
                                            model.data_cov.data_ptr(), sc.small.data_ptr(), _stream()))
+        if self.dp is not None and self.dp[1] > 1 and len(self.dp) > 3:
+            # the moments are accumulated with float atomics (order-dependent last bits): rank 0's values are
+            # THE whitening constants of every replica
+            self.dp[3](model.data_mean)
+            self.dp[3](model.data_cov)
         loss_values = np.zeros(num_epochs, np.float32)
         rng = np.asarray(rng, dtype=np.uint32)
         it = range(num_epochs)

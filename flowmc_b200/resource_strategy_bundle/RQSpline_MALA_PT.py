@@ -55,7 +55,8 @@ class RQSpline_MALA_PT_Bundle(RQSpline_MALA_Bundle):
             n_steps=n_tempered_steps, tempered_logpdf_name="tempered_logpdf", kernel_name="local_sampler",
             tempered_buffer_names=["tempered_positions", "temperatures"], state_name="sampler_state", verbose=verbose)
         if chain_shard is not None:
-            parallel_tempering_strat.set_chain_shard(chain_shard.offset, chain_shard.n_chains_global)
+            parallel_tempering_strat.set_chain_shard(chain_shard.offset, chain_shard.n_chains_global,
+                                                     chain_shard.all_reduce)
 
         def initialize_tempered_positions(rng_key, resources, initial_position, data):
             # every rung starts at the chain's initial position (RQSpline_MALA_PT.py:283-287)

@@ -43,9 +43,13 @@ class ParallelTempering(Strategy):
         self.state_name = state_name
         # global chain shard owned by this process: (offset, n_chains_global) or None = all chains
         self.chain_shard = None
+        self.all_reduce = None
 
-    def set_chain_shard(self, offset: int, n_chains_global: int):
+    def set_chain_shard(self, offset: int, n_chains_global: int, all_reduce=None):
+        """``all_reduce(tensor)`` (sum over ranks, in place): makes the temperature adaptation use the exchange
+        acceptance of ALL chains, so every rank adapts the same ladder as a single-GPU run."""
         self.chain_shard = (int(offset), int(n_chains_global))
+        self.all_reduce = all_reduce
 
     def __call__(self, rng_key, resources, initial_position, data):
         rng_key, subkey = frandom.split(rng_key)                       # parallel_tempering.py:73 (subkey unused there too)
@@ -141,8 +145,17 @@ class ParallelTempering(Strategy):
         """float32 arithmetic of the reference on the n_temps ladder values (host)."""
         t = np.asarray(torch.as_tensor(temperatures).detach().cpu(), dtype=np.float32)
         acc = torch.as_tensor(do_accept, dtype=torch.float32)
-        acceptance_rate = acc.mean(dim=0).detach().cpu().numpy().astype(np.float32)
-        damping_factor = (np.float32(100.0 / acc.shape[0]) * (acceptance_rate[:-1] - acceptance_rate[1:])).astype(np.float32)
+        n_chains = acc.shape[0]
+        if self.chain_shard is not None and self.all_reduce is not None:
+            # mean over ALL chains (parallel_tempering.py:421): accept flags are 0 / 1, so the per-rung counts add
+            # exactly in float32 (< 2^24 chains) and every rank gets the single-GPU acceptance rate
+            counts = acc.sum(dim=0)
+            self.all_reduce(counts)
+            n_chains = self.chain_shard[1]
+            acceptance_rate = (counts / np.float32(n_chains)).detach().cpu().numpy().astype(np.float32)
+        else:
+            acceptance_rate = acc.mean(dim=0).detach().cpu().numpy().astype(np.float32)
+        damping_factor = (np.float32(100.0 / n_chains) * (acceptance_rate[:-1] - acceptance_rate[1:])).astype(np.float32)
         new_t = t.copy()
         for i in range(1, t.shape[0] - 1):
             new_t[i] = new_t[i - 1] + (t[i] - t[i - 1]) * np.exp(damping_factor[i - 1], dtype=np.float32)

@@ -3,9 +3,9 @@
 Same constructor and call contract.  The training set is selected on the device: finite rows of
 the positions buffer, the last ``history_window`` of them per chain, ``n_max_examples`` drawn with
 jax.random.choice-compatible indices (train_model.py:66-81).  With a chain shard set
-(``set_chain_shard``) each rank gathers the rows of its own chains and an all-gather (NCCL
-all-reduce of the disjointly-filled buffer) gives every rank the full training set, after which
-``NFModel.train`` runs data-parallel.
+(``set_chain_shard``) each rank gathers the rows of its own chains and an NCCL all-gather of the
+per-rank row blocks gives every rank the full training set, after which ``NFModel.train`` runs
+data-parallel.
 """
 from __future__ import annotations
 
@@ -41,10 +41,24 @@ class TrainModel(Strategy):
         self.verbose = verbose
         self.history_window = history_window
         self.chain_shard = None   # (offset, n_chains_global, all_reduce) for multi-GPU runs
+        self.shard = None
         self.last_training_data = None
 
-    def set_chain_shard(self, offset: int, n_chains_global: int, all_reduce):
+    def set_chain_shard(self, offset: int, n_chains_global: int, all_reduce, shard=None):
+        """``shard`` (a ``flowmc_b200.parallel.ChainShard``) enables the all-gather assembly of the training set;
+        without it the rows are assembled by a sum-all-reduce of a zero-filled buffer (same result)."""
         self.chain_shard = (int(offset), int(n_chains_global), all_reduce)
+        self.shard = shard
+
+    def _assemble_all_gather(self, buf, rowmap, n_total, d, window, lo, idx, stream):
+        """All-gather of per-rank row blocks.  Every rank knows the whole ``choice`` draw ``idx``; rows are
+        grouped by owning rank (stable), each rank gathers the rows of its own chains into its block, one
+        ``all_gather_into_tensor`` moves every block to every rank, and the blocks are put back in draw order."""
+        def gather_own(my_idx, block):
+            check(lib.flowmc_gather_training_rows(buf.data_ptr(), rowmap.data_ptr(), n_total, d, window, lo,
+                                                  self.shard.offset, self.shard.offset + buf.shape[0],
+                                                  my_idx.data_ptr(), int(my_idx.numel()), block.data_ptr(), stream))
+        return self.shard.assemble_rows(idx, window, d, gather_own)
 
     def select_training_data(self, rng_key, buf: torch.Tensor):
         """train_model.py:66-81 -> (rng_key after the first split, training_data [n_max_examples, d])."""
@@ -74,6 +88,8 @@ class TrainModel(Strategy):
             m = int(self.n_max_examples)
             idx = torch.empty(m, dtype=torch.int32, device=dev)
             check(lib.flowmc_random_choice(subkey.ctypes.data_as(_u32p), n_glob * window, m, idx.data_ptr(), stream))
+            if all_reduce is not None and self.shard is not None and self.shard.world_size > 1:
+                return rng_key, self._assemble_all_gather(buf, rowmap, n_total, d, window, lo, idx, stream)
             out = torch.zeros((m, d), dtype=torch.float32, device=dev) if all_reduce is not None else \
                 torch.empty((m, d), dtype=torch.float32, device=dev)
             check(lib.flowmc_gather_training_rows(buf.data_ptr(), rowmap.data_ptr(), n_total, d, window, lo, offset,

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define FLOWMC_ABI_VERSION 2
+#define FLOWMC_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define FLOWMC_API __attribute__((visibility("default")))
@@ -104,12 +104,24 @@ typedef struct FlowmcLocalParams {
   const float* beta;      /* FLOWMC_KERNEL_MALA_TEMPERED: device [n_chains] inverse temperatures 1 / T (NULL = 1) */
   const float* prior;     /* FLOWMC_KERNEL_MALA_TEMPERED: device [4, d] = c, m, lo, hi of
                            * log_prior(x) = -sum_j c_j (x_j - m_j)^2 inside [lo, hi], -inf outside; NULL = flat 0 */
+  int force_n_seg;        /* time slicing: 0 = automatic (slice when there are more chain groups than resident CTA
+                           * slots); > 1 = cut the n_steps into this many segments regardless; < 0 = never slice.
+                           * Results do not depend on it (tests/test_gpu_local_sliced.py) */
+  int slots_override;     /* 0 = the device's resident CTA slots; > 0 = plan the rounds as if there were this many
+                           * (test hook: forces multi-round launches with a handful of chains) */
 } FlowmcLocalParams;
 
 /* bytes of `workspace` that flowmc_local_steps can use for (n_chains, d, layout_hint) */
 FLOWMC_API int64_t flowmc_local_steps_workspace_bytes(int64_t n_chains, int d, int layout_hint);
 
-/* Runs n_steps of one local kernel for n_chains chains in ONE persistent kernel launch and
+/* The launch plan flowmc_local_steps would use for (kind, target, n_chains, d, n_steps, params), without launching:
+ * plan[12] (host) = {layout index, G lanes per chain, DPL dims per lane, VEC store width, chain groups, resident CTA
+ * slots, CTAs per SM, static shared memory per CTA, n_seg, seg_len, n_rounds (= kernel launches), CTAs per round}. */
+FLOWMC_API int flowmc_local_steps_plan(int kind, int target_id, int64_t n_chains, int d, int n_steps,
+                                       const FlowmcLocalParams* params, int plan[12]);
+
+/* Runs n_steps of one local kernel for n_chains chains in ONE persistent kernel launch (or, when there are more
+ * chain groups than resident CTA slots, one launch per resident wave of (time segment, chain group) work items) and
  * writes the thinned samples straight into the (chain-major) sampler buffers at `cursor`:
  *   pos_buf  device [n_chains, n_total, d]      lp_buf, acc_buf  device [n_chains, n_total]
  * key:      host, the strategy-level rng_key; key_out: host, the rng_key the strategy returns.

@@ -233,8 +233,9 @@ static float mvn_scalar(const float* x, const float* mean, int d, float cov) {
   return -0.5f * yy / cov - (float)d / 2.0f * (1.8378770664093453f + logf(cov));
 }
 
+/* one kernel.kernel() application; dbg (optional) receives {MH log-ratio, log(uniform)} of the accept test */
 static int one_step(const KernelCfg* k, int tgt, const float* data, int d, uint32_t s0, uint32_t s1, float* x,
-                    float* lp_io) {
+                    float* lp_io, float* dbg) {
   uint32_t key1[2], key2[2], bits[MAXD], a, b;
   float z[MAXD], prop[MAXD], g0[MAXD], g1[MAXD], m0[MAXD], m1[MAXD];
   threefry2x32(s0, s1, 0, 0, &key1[0], &key1[1]);
@@ -260,12 +261,14 @@ static int one_step(const KernelCfg* k, int tgt, const float* data, int d, uint3
     ratio = ratio - mvn_scalar(prop, m0, d, dt2);
     ratio = ratio + mvn_scalar(x, m1, d, dt2);
     acc = log_u < ratio;
+    if (dbg) dbg[0] = ratio;
     if (acc) memcpy(x, prop, sizeof(float) * d);
     *lp_io = acc ? lp1 : lp0;
   } else if (k->kind == 2) {
     for (int j = 0; j < d; ++j) prop[j] = x[j] + z[j] * k->step_size;
     float lp1 = logp_grad(tgt, data, prop, d, g1, 0);
     acc = log_u < (lp1 - *lp_io);
+    if (dbg) dbg[0] = lp1 - *lp_io;
     if (acc) {
       memcpy(x, prop, sizeof(float) * d);
       *lp_io = lp1;
@@ -294,11 +297,13 @@ static int one_step(const KernelCfg* k, int tgt, const float* data, int d, uint3
     for (int j = 0; j < d; ++j) kin1 += p[j] * p[j] * k->colsum[j];
     const float ham = -lp1 + 0.5f * kin1;
     acc = log_u < (H - ham);
+    if (dbg) dbg[0] = H - ham;
     if (acc) {
       memcpy(x, xs, sizeof(float) * d);
       *lp_io = lp1;
     }
   }
+  if (dbg) dbg[1] = log_u;
   return acc;
 }
 
@@ -327,11 +332,21 @@ int ref_num_threads(void) {
 #endif
 }
 
-/* take_steps.py:60-144: returns 0 on success.  pos [n, n_out, d], lp/acc [n, n_out], last [n, d]. */
+/* torchrun exports OMP_NUM_THREADS=1: the benchmark arm sets the thread count explicitly */
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
+/* take_steps.py:60-144: returns 0 on success.  pos [n, n_out, d], lp/acc [n, n_out], last [n, d]; ratio_out / logu_out
+ * (optional, [n, n_out]): the two sides of the accept test of every stored step (near-tie accounting in the tests). */
 int ref_take_serial_steps(int kind, int tgt, const float* data, const uint32_t* key, const float* x0, int64_t n,
                           int d, int n_steps, int thinning, int64_t chain_offset, float step_size, int n_leapfrog,
                           const float* chol, const float* colsum, uint32_t* key_out, float* pos, float* lp_out,
-                          float* acc_out, float* last) {
+                          float* acc_out, float* last, float* ratio_out, float* logu_out) {
   if (d > MAXD || d < 1) return -1;
   KernelCfg cfg = {kind, step_size, n_leapfrog, chol, colsum};
   uint32_t sub[2];
@@ -351,9 +366,12 @@ int ref_take_serial_steps(int kind, int tgt, const float* data, const uint32_t* 
       threefry2x32(kc[0], kc[1], 0, 1, &s[0], &s[1]);
       kc[0] = nk[0];
       kc[1] = nk[1];
-      int acc = one_step(&cfg, tgt, data, d, s[0], s[1], x, &lp);
+      float dbg[2];
+      int acc = one_step(&cfg, tgt, data, d, s[0], s[1], x, &lp, dbg);
       if (t % thinning == 0) {
         const int o = t / thinning;
+        if (ratio_out) ratio_out[(size_t)c * n_out + o] = dbg[0];
+        if (logu_out) logu_out[(size_t)c * n_out + o] = dbg[1];
         if (pos) memcpy(pos + ((size_t)c * n_out + o) * d, x, sizeof(float) * d);
         if (lp_out) lp_out[(size_t)c * n_out + o] = lp;
         if (acc_out) acc_out[(size_t)c * n_out + o] = (float)acc;

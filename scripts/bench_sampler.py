@@ -48,30 +48,18 @@ class Timed:
         return out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--chains", type=int, default=65536)
-    ap.add_argument("--dim", type=int, default=64)
-    ap.add_argument("--quick", action="store_true")
-    args = ap.parse_args()
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
+def run_sampler(dev, rank, world, n_chains=65536, d=64, quick=False):
+    """One full C5 run (strong scaling: ``n_chains`` in TOTAL, sharded over ``world`` ranks).  Collective: every rank
+    must call it.  Returns the result dict (identical on every rank apart from rank-0 phase times)."""
     from flowmc_b200 import random as frandom, targets as T
     from flowmc_b200.parallel import ChainShard
     from flowmc_b200.resource_strategy_bundle.RQSpline_MALA import RQSpline_MALA_Bundle
     from flowmc_b200.Sampler import Sampler
 
-    d, n_chains = args.dim, args.chains
     cfg = dict(n_local_steps=50, n_global_steps=10, n_training_loops=4, n_production_loops=4, n_epochs=5,
                mala_step_size=0.1, rq_spline_hidden_units=[128, 128], rq_spline_n_bins=8, rq_spline_n_layers=8,
                learning_rate=1e-3, batch_size=16384, n_max_examples=1048576)
-    if args.quick:
+    if quick:
         cfg.update(n_training_loops=2, n_production_loops=2, n_epochs=2, n_max_examples=131072)
     rs = np.random.RandomState(0)
     mu = np.zeros((8, d), np.float32)
@@ -85,9 +73,10 @@ def main():
     x0 = frandom.normal(sub, (n_chains, d), device=dev)
     if shard is not None:
         x0 = shard.slab(x0).contiguous()
-    # warm-up: a miniature run of the same bundle (same target, dimension and flow shape, 256 chains) so that CUDA's
-    # lazy module loading (~50 ms for the first launch of each kernel) and the NCCL communicators are not timed
-    wcfg = dict(cfg, n_training_loops=1, n_production_loops=1, n_epochs=1, batch_size=128, n_max_examples=256)
+    # warm-up: a miniature run of the same bundle (same target, dimension and flow shape, 256 chains per rank) so that
+    # CUDA's lazy module loading (~50 ms for the first launch of each kernel) and the NCCL communicators are not timed
+    wcfg = dict(cfg, n_training_loops=1, n_production_loops=1, n_epochs=1, batch_size=128 * world,
+                n_max_examples=256 * world)
     wshard = ChainShard(256 * world, rank, world) if world > 1 else None
     wx0 = frandom.normal(frandom.PRNGKey(1), (256 * world, d), device=dev)
     wbundle = RQSpline_MALA_Bundle(frandom.PRNGKey(2), 256 * world, d, target, chain_shard=wshard, **wcfg)
@@ -103,18 +92,26 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    sampler.sample(x0, {})
     torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    sampler.sample(x0, {})
+    ev1.record()
+    torch.cuda.synchronize()
+    wall_host = time.perf_counter() - t0
+    tt = torch.tensor([ev0.elapsed_time(ev1) * 1e-3], device=dev, dtype=torch.float64)   # device time, max over ranks
     if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.barrier()
-    wall = time.perf_counter() - t0
+    wall = float(tt.item())
     ms = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in acc.items()}
     res = sampler.resources
     loops = cfg["n_training_loops"] + cfg["n_production_loops"]
     local_steps = n_chains * cfg["n_local_steps"] * loops
     global_steps = n_chains * cfg["n_global_steps"] * loops
-    train_rows = cfg["n_training_loops"] * cfg["n_epochs"] * (cfg["n_max_examples"] // cfg["batch_size"]) * cfg["batch_size"]
+    train_steps = cfg["n_training_loops"] * cfg["n_epochs"] * (cfg["n_max_examples"] // cfg["batch_size"])
+    train_rows = train_steps * cfg["batch_size"]
     ga = res["global_accs_production"].data
     la = res["local_accs_production"].data
     pos = res["positions_production"].data
@@ -124,18 +121,40 @@ def main():
         t = torch.tensor([ess], device=dev, dtype=torch.float64)
         dist.all_reduce(t)
         ess = float(t.item())
+    return {
+        "workload": f"C5: full Sampler (MALA + NFProposal + TrainModel), {d}-D 8-component mixture, {n_chains} chains "
+                    f"in total over {world} GPU(s) (strong scaling), flow 8x[128,128]x8",
+        "config": cfg, "n_gpus": world, "wall_s": wall, "wall_s_host_rank0": wall_host, "phase_ms_rank0": ms,
+        "timing": "CUDA events around Sampler.sample on each rank, max over ranks",
+        "local_chain_steps_per_s": local_steps / (ms["local_stepper"] * 1e-3),
+        "global_chain_steps_per_s": global_steps / (ms["global_stepper"] * 1e-3),
+        "flow_train_samples_per_s": train_rows / (ms["model_trainer"] * 1e-3),
+        "flow_train_ms_per_step": ms["model_trainer"] / train_steps,
+        "flow_train_parallelism": ("data-parallel: batch split over ranks, gradient + loss all-reduce (NCCL)"
+                                   if world > 1 else "single GPU"),
+        "sampler_chain_steps_per_s": (local_steps + global_steps) / wall,
+        "ess_per_s": ess / wall,
+        "global_acceptance": float(ga[torch.isfinite(ga)].mean()), "local_acceptance": float(la[torch.isfinite(la)].mean()),
+        "final_loss": float(res["loss_buffer"].data[-1]), "first_loss": float(res["loss_buffer"].data[0]),
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--chains", type=int, default=65536)
+    ap.add_argument("--dim", type=int, default=64)
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    out = run_sampler(dev, rank, world, args.chains, args.dim, args.quick)
     if rank == 0:
-        print(json.dumps({
-            "workload": f"full Sampler (MALA + NFProposal + TrainModel), {d}-D 8-component mixture, {n_chains} chains, "
-                        f"{world} GPU(s)", "config": cfg, "wall_s": wall, "phase_ms_rank0": ms,
-            "local_chain_steps_per_s": local_steps / (ms["local_stepper"] * 1e-3),
-            "global_chain_steps_per_s": global_steps / (ms["global_stepper"] * 1e-3),
-            "flow_train_samples_per_s": train_rows / (ms["model_trainer"] * 1e-3),
-            "sampler_chain_steps_per_s": (local_steps + global_steps) / wall,
-            "ess_per_s": ess / wall,
-            "global_acceptance": float(ga[torch.isfinite(ga)].mean()), "local_acceptance": float(la[torch.isfinite(la)].mean()),
-            "final_loss": float(res["loss_buffer"].data[-1]), "first_loss": float(res["loss_buffer"].data[0]),
-        }), flush=True)
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -88,3 +88,43 @@ def teacher_forced(kernel, logpdf, data, dbg, steps, rtol=RTOL, tie_tol=1e-4):
         assert (same | near).all(), f"step {t}: accept decision differs away from a tie"
         assert_close(p.cpu().numpy()[same], info["x_out"][same], f"step {t} positions", rtol)
         assert_close(l.cpu().numpy()[same], info["lp_out"][same], f"step {t} log_probs", rtol)
+
+
+def compare_chains_vec(gpu, ora, ratio, log_u, max_diverged_frac=0.01, rtol=RTOL_TRAJ, tie_tol=1e-4, what=""):
+    """Vectorised ``compare_chains`` for runs at the BASELINE scales (millions of chain-steps).
+
+    gpu / ora = (positions[n,T,d], log_probs[n,T], accepts[n,T]); ratio / log_u [n,T] = the two sides of the
+    oracle's accept test at every stored step.  Same contract: a chain whose flags differ from the oracle's must
+    have its FIRST difference at a near-tie; everything before it must agree within ``rtol``; the number of such
+    chains is bounded.  Returns (number of diverged chains, max position error before divergence)."""
+    gp, gl, ga = gpu
+    op, ol, oa = ora
+    n, T = oa.shape
+    differs = ga != oa
+    first = np.where(differs.any(axis=1), differs.argmax(axis=1), T)          # first differing step per chain
+    bad = np.nonzero(first < T)[0]
+    if bad.size:
+        r = ratio[bad, first[bad]].astype(np.float64)
+        u = log_u[bad, first[bad]].astype(np.float64)
+        near = np.abs(r - u) <= tie_tol * np.maximum(1.0, np.abs(r))
+        assert near.all(), (f"{what}: {(~near).sum()} chains differ from the oracle away from a near-tie, e.g. chain "
+                            f"{bad[~near][0]} step {first[bad[~near][0]]} ratio {r[~near][0]} log_u {u[~near][0]}")
+    assert bad.size <= max(1, int(max_diverged_frac * n)), f"{what}: {bad.size} of {n} chains diverged"
+    valid = np.arange(T)[None, :] < first[:, None]                              # steps before the divergence
+    scale_l = max(1.0, float(np.abs(ol[np.isfinite(ol)]).max()))
+    el = np.abs(gl.astype(np.float64) - ol) * valid
+    assert np.array_equal(np.isfinite(gl) | ~valid, np.isfinite(ol) | ~valid), f"{what}: log-prob finite masks differ"
+    el = np.where(np.isfinite(el), el, 0.0)
+    tol_l = rtol * np.maximum(np.abs(ol), scale_l)
+    assert (el <= tol_l).all(), f"{what}: log-probs beyond rtol={rtol}: max err {el.max():.3e} (scale {scale_l:.3g})"
+    scale_p = max(1.0, float(np.abs(op).max()))
+    worst = 0.0
+    step = max(1, (1 << 24) // max(1, T * op.shape[2]))                          # ~64 MB slabs
+    for c0 in range(0, n, step):
+        sl = slice(c0, min(n, c0 + step))
+        ep = np.abs(gp[sl].astype(np.float64) - op[sl]) * valid[sl, :, None]
+        tol_p = rtol * np.maximum(np.abs(op[sl]), scale_p)
+        assert (ep <= tol_p).all(), (f"{what}: positions beyond rtol={rtol} in chains {c0}..: max err {ep.max():.3e} "
+                                     f"(scale {scale_p:.3g})")
+        worst = max(worst, float(ep.max()))
+    return int(bad.size), worst

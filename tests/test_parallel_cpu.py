@@ -52,6 +52,38 @@ def _worker(rank, world, port, ret):
         shard.all_reduce(out)
         assert np.array_equal(out.numpy(), want)
 
+        # 2b. the product's all-gather assembly (ChainShard.assemble_rows) with a numpy gather standing in for
+        #     flowmc_gather_training_rows: same rows in the same order as the single-process selection
+        pop = buf[:, -window:].reshape(-1, d)
+
+        def gather_own(my_idx, block):
+            ch = my_idx.numpy() // window
+            assert ((ch >= shard.offset) & (ch < shard.offset + shard.n_local)).all()
+            block[:my_idx.numel()] = torch.from_numpy(pop[my_idx.numpy()])
+        got = shard.assemble_rows(torch.from_numpy(idx.astype(np.int32)), window, d, gather_own)
+        assert np.array_equal(got.numpy(), want)
+
+        # 2c. ParallelTempering._adapt_temperature: per-rung accept counts summed over ranks -> the ladder of the
+        #     unsharded run on every rank (parallel_tempering.py:400-436)
+        from flowmc_b200.strategy.parallel_tempering import ParallelTempering
+        rs = np.random.RandomState(0)
+        acc_full = (rs.rand(n_chains, 4) < np.array([0.2, 0.5, 0.8, 0.4])).astype(np.float32)
+        temps = torch.tensor([1.0, 2.0, 4.0, 8.0, 16.0])
+        pt1 = ParallelTempering(n_steps=1, tempered_logpdf_name="t", kernel_name="k",
+                                tempered_buffer_names=["a", "b"], state_name="s")
+        want_t = pt1._adapt_temperature(temps, torch.from_numpy(acc_full))
+        ptr = ParallelTempering(n_steps=1, tempered_logpdf_name="t", kernel_name="k",
+                                tempered_buffer_names=["a", "b"], state_name="s")
+        ptr.set_chain_shard(shard.offset, n_chains, shard.all_reduce)
+        got_t = ptr._adapt_temperature(temps, shard.slab(torch.from_numpy(acc_full)))
+        assert torch.equal(got_t, want_t), (got_t, want_t)
+        assert not torch.equal(want_t, temps)
+
+        # 2d. broadcast keeps replicas' whitening constants identical
+        mom = torch.full((3,), float(rank + 1))
+        shard.broadcast(mom)
+        assert torch.equal(mom, torch.ones(3))
+
         # 3. data-parallel gradient: per-rank slices scaled by 1/global batch, summed == full-batch gradient
         p = oflow.init_params(rng.PRNGKey(1), d, 2, [8, 8], 4)
         x = want[:32]
