@@ -105,9 +105,7 @@ def _load() -> C.CDLL:
         "flowmc_buffer_finite_rows": (i32, [vp, i64, i64, i32, vp, vp, vp, vp]),
         "flowmc_gather_training_rows": (i32, [vp, vp, i64, i32, i32, i32, i64, i64, vp, i64, vp, vp]),
         "flowmc_data_mean_cov": (i32, [vp, i64, i32, vp, vp, vp, vp]),
-        "flowmc_debug_tc_timing": (None, [vp]),
-        "flowmc_debug_tc_gemm": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
-        "flowmc_debug_tc_gemm_pair": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+        "flowmc_trace_tc_timeline": (None, [vp]),
         "flowmc_nf_global_steps_workspace_bytes": (i64, [i64, i32, i32]),
         "flowmc_nf_global_steps": (i32, [C.POINTER(FlowDesc), vp, i32, vp, u32p, vp, vp, vp, vp, i64, i64, i64, i32,
                                          i32, i64, i64, C.POINTER(GlobalParams), u32p, vp, vp]),
@@ -126,6 +124,21 @@ def check(rc: int) -> int:
     if rc < 0:
         raise FlowmcError(f"flowmc_b200 error {rc}: {lib.flowmc_last_error().decode()}")
     return rc
+
+
+def load_test_lib() -> C.CDLL:
+    """libflowmc_b200_test.so: probe kernels for the tcgen05 building blocks (include/flowmc_b200_test.h) -- test
+    scaffolding kept out of the product library."""
+    path = _LIB_PATH.parent / "libflowmc_b200_test.so"
+    if not path.exists():
+        raise ImportError(f"{path} not found: run `python -m flowmc_b200.build`")
+    t = C.CDLL(str(path), mode=C.RTLD_GLOBAL)
+    vp, i32 = C.c_void_p, C.c_int
+    for name in ("flowmc_test_tc_gemm", "flowmc_test_tc_gemm_pair"):
+        fn = getattr(t, name)
+        fn.restype = i32
+        fn.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
+    return t
 
 
 def load_plugin(path: str) -> None:

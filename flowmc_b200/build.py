@@ -18,6 +18,7 @@ CSRC = ROOT / "csrc"
 BUILD = REPO / "build" / "obj"
 LIBDIR = ROOT / "lib"
 LIB = LIBDIR / "libflowmc_b200.so"
+TEST_LIB = LIBDIR / "libflowmc_b200_test.so"   # csrc/testlib/*.cu: probe kernels for tests, not product code
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -31,7 +32,30 @@ def _headers_mtime() -> float:
 
 
 def sources() -> list[Path]:
-    return sorted(CSRC.rglob("*.cu"))
+    """Product sources: every .cu under csrc/ except the test scaffolding in csrc/testlib/."""
+    return sorted(p for p in CSRC.rglob("*.cu") if "testlib" not in p.relative_to(CSRC).parts)
+
+
+def test_sources() -> list[Path]:
+    return sorted((CSRC / "testlib").glob("*.cu"))
+
+
+def _compile_host(src: Path, verbose: bool) -> Path:
+    """Host-only C++ sources of the product library (the XLA-FFI shim: an empty translation unit unless jaxlib's
+    xla/ffi/api/ffi.h is on the include path -- add it with FLOWMC_XLA_FFI_INCLUDE)."""
+    obj = BUILD / src.relative_to(CSRC).with_suffix(".o")
+    obj.parent.mkdir(parents=True, exist_ok=True)
+    if (not obj.exists()) or obj.stat().st_mtime < max(src.stat().st_mtime, _headers_mtime()):
+        inc = ["-I", str(REPO / "include"), "-I", "/usr/local/cuda/include"]
+        if os.environ.get("FLOWMC_XLA_FFI_INCLUDE"):
+            inc += ["-I", os.environ["FLOWMC_XLA_FFI_INCLUDE"]]
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", *inc, "-c", str(src), "-o", str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed for {src}:\n{r.stdout}{r.stderr}")
+        if verbose:
+            print(f"[flowmc_b200.build] compiled {src.relative_to(CSRC)}")
+    return obj
 
 
 def _compile(src: Path, hdr_m: float, verbose: bool) -> tuple[Path, str]:
@@ -64,6 +88,8 @@ def build(verbose: bool = True, jobs: int | None = None) -> Path:
     jobs = jobs or min(len(srcs), os.cpu_count() or 4)
     with ThreadPoolExecutor(max_workers=jobs) as ex:
         objs = [o for o, _ in ex.map(lambda s: _compile(s, hdr_m, verbose), srcs)]
+        test_objs = [o for o, _ in ex.map(lambda s: _compile(s, hdr_m, verbose), test_sources())]
+    objs += [_compile_host(p, verbose) for p in sorted(CSRC.glob("*.cc"))]
     newest = max(o.stat().st_mtime for o in objs)
     if (not LIB.exists()) or LIB.stat().st_mtime < newest:
         cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *map(str, objs)]
@@ -72,6 +98,15 @@ def build(verbose: bool = True, jobs: int | None = None) -> Path:
             raise RuntimeError(f"link failed:\n{r.stdout}{r.stderr}")
         if verbose:
             print(f"[flowmc_b200.build] linked {LIB}")
+    if test_objs and ((not TEST_LIB.exists()) or TEST_LIB.stat().st_mtime < max(
+            [LIB.stat().st_mtime] + [o.stat().st_mtime for o in test_objs])):
+        cmd = [NVCC, *ARCH, "-shared", "-o", str(TEST_LIB), *map(str, test_objs), "-L", str(LIBDIR), "-lflowmc_b200",
+               "-Xlinker", "-rpath=$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}{r.stderr}")
+        if verbose:
+            print(f"[flowmc_b200.build] linked {TEST_LIB}")
     return LIB
 
 

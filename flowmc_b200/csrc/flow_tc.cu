@@ -786,7 +786,7 @@ static int dispatch_tc(const FlowmcFlowDesc& D, const TcProgram& PR, const TcArg
   return FLOWMC_ERR_UNSUPPORTED;
 }
 
-static long long* g_tc_timing = nullptr;  // diagnostics hook (flowmc_debug_tc_timing)
+static long long* g_tc_timing = nullptr;  // diagnostics hook (flowmc_trace_tc_timeline)
 
 // true if the descriptor asks for (and the model shape allows) the tensor-core path
 bool flow_tc_enabled(const FlowmcFlowDesc& D) { return D.tc_image != nullptr && D.tc_terms != 0 && tc_supported(D); }
@@ -830,7 +830,7 @@ extern "C" {
 
 // diagnostics: device buffer of 3 * 256 int64 that CTA 0 of the next tensor-core flow launches stamps with clock64()
 // (NULL switches it off).  Not thread-safe; used by scripts/tc_timeline.py only.
-void flowmc_debug_tc_timing(long long* buf) {
+void flowmc_trace_tc_timeline(long long* buf) {
   flowmc::g_tc_timing = buf;
   flowmc::flow_backward_tc_set_timing(buf ? buf + 3 * 256 : nullptr);  // 4th row: backward epilogue thread 0
 }

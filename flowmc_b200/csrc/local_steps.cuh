@@ -23,16 +23,16 @@
 // the serial k_c chain runs once per chunk, then the 32 steps' (s, key1, key2, u) are computed
 // one step per lane and parked in shared memory.  Bits are identical to jax.random's.
 //
-// Time slicing.  All chains cost the same, so with more warps than resident slots a plain grid
-// runs ceil(waves) full-length waves.  Instead the step range is cut into S segments and the
-// (segment, group) work items, numbered item = segment * n_groups + group, run as ROUNDS: launch r
+// Time slicing (optional).  With more warps than resident slots a plain grid runs in waves; alternatively the
+// step range can be cut into S segments and the (segment, group) work items, numbered item = segment * n_groups + group, run as ROUNDS: launch r
 // holds the items [r * R, (r + 1) * R) with R = min(slots, n_groups) CTAs, i.e. exactly one resident
 // wave.  Item (s, g) runs steps [s*Ls, (s+1)*Ls) of group g and leaves the chain state (position,
 // cached gradient, log-prob, chain key) in a small global workspace for item (s+1, g), which lies
 // n_groups >= R items later and therefore always in a LATER launch on the same stream: the
 // kernel boundary is the only synchronisation (no flags, no spinning, no fences), so the schedule
-// and its duration are deterministic.  The host picks S to minimise ceil(groups*S/R) * (Ls + c);
-// S = 1 (one launch) when everything is resident.
+// and its duration are deterministic.  Slicing is OPT-IN (FlowmcLocalParams.force_n_seg > 1): on B200
+// the plain one-launch grid measured faster at every BASELINE shape (see launch_local_one) -- the kernel is
+// issue-bound, so a partially filled last wave still runs near full rate.
 //
 // The gradient of the current point is carried across steps (the reference recomputes it every
 // step, MALA.py:59 -- same value, half the work).
@@ -604,10 +604,15 @@ __host__ inline int64_t local_workspace_bytes(int64_t n_chains, int d, int hint)
 // Resident CTA slots of one kernel instantiation on the current device.  The shared-memory carve-out is pinned to what
 // MINB CTAs per SM need (the driver's default heuristic may pick a smaller one and halve the occupancy), then the
 // occupancy is queried once per device.
+constexpr int kMaxDev = 64;
+struct SlotCache {  // one per kernel instantiation (a static local of launch_local_one), indexed by device
+  int slots[kMaxDev], per_sm_c[kMaxDev], smem_c[kMaxDev];
+};
 template <class K>
-inline void local_slots(K kern, int minb, int* slots_out, int* per_sm_out, int* smem_out) {
-  constexpr int kMaxDev = 64;
-  static int slots[kMaxDev] = {0}, per_sm_c[kMaxDev] = {0}, smem_c[kMaxDev] = {0};
+inline void local_slots(K kern, int minb, SlotCache& sc, int* slots_out, int* per_sm_out, int* smem_out) {
+  int (&slots)[kMaxDev] = sc.slots;
+  int (&per_sm_c)[kMaxDev] = sc.per_sm_c;
+  int (&smem_c)[kMaxDev] = sc.smem_c;
   int dev = 0;
   cudaGetDevice(&dev);
   const int di = (dev >= 0 && dev < kMaxDev) ? dev : 0;
@@ -641,7 +646,8 @@ inline int launch_local_one(const LocalArgs* a, cudaStream_t stream) {
   Slice sl{1, a->n_steps, (int)n_groups, 0, nullptr};
 
   int slots = 0, per_sm = 0, smem = 0;
-  local_slots(kern, MINB, &slots, &per_sm, &smem);
+  static SlotCache slot_cache = {};  // per instantiation: occupancy differs between layouts / targets / kinds
+  local_slots(kern, MINB, slot_cache, &slots, &per_sm, &smem);
   if (a->slots_override > 0) slots = a->slots_override;  // tests: force rounds with small grids
   const int64_t need = n_groups * L::NSTATE * 32 * 4;
   const bool can_slice = a->workspace != nullptr && a->workspace_bytes >= need && a->step_keys == nullptr;
@@ -653,24 +659,11 @@ inline int launch_local_one(const LocalArgs* a, cudaStream_t stream) {
     const int s = a->force_n_seg < a->n_steps ? a->force_n_seg : a->n_steps;
     sl.seg_len = (a->n_steps + s - 1) / s;
     sl.n_seg = (a->n_steps + sl.seg_len - 1) / sl.seg_len;
-  } else if (a->force_n_seg == 0) {
-    const int max_seg = a->n_steps / kChunk;  // keep segments >= one key-schedule chunk
-    if (n_groups > slots && max_seg >= 2 && can_slice) {
-      // choose S minimising (rounds of resident CTAs) x (segment length)
-      int64_t best_cost = ((n_groups + slots - 1) / slots) * (int64_t)a->n_steps;
-      for (int s = 2; s <= (max_seg < 48 ? max_seg : 48); ++s) {
-        const int len = (a->n_steps + s - 1) / s;
-        const int s_eff = (a->n_steps + len - 1) / len;
-        const int64_t rounds = (n_groups * s_eff + slots - 1) / slots;
-        const int64_t cost = rounds * (len + 2);  // +2: per-round launch + hand-off overhead in step units
-        if (cost < best_cost) {
-          best_cost = cost;
-          sl.n_seg = s_eff;
-          sl.seg_len = len;
-        }
-      }
-    }
-  }  // force_n_seg < 0: never slice
+  }
+  // force_n_seg <= 0: one launch.  Measured on B200 (profiles/r02_slice_sweep.jsonl), the plain grid beats every sliced
+  // plan at the BASELINE shapes -- C2 4.88 vs 5.09 ms, C3 7.41 vs 8.44 ms: the kernel is issue-bound, so the last,
+  // partially filled wave of a plain grid still runs near full rate (fewer warps per SM, each faster), while every
+  // round of a sliced plan pays a drain + launch (~45 us).  Slicing therefore stays an explicit option.
   if (sl.n_seg > 1) sl.state = reinterpret_cast<float*>(a->workspace);
   // a round = one resident wave; item (s, g) depends on item (s-1, g) = n_groups items earlier, which is in an earlier
   // round as long as a round holds at most n_groups items

@@ -1,12 +1,14 @@
 // Probe / unit-test kernel for the tcgen05 building blocks in tc_common.cuh: out[128, N] = A[128, K] W[N, K]^T with
 // A written to TMEM by the epilogue warps (tcgen05.st), W pre-packed into swizzled K-major stages and brought in
 // with cp.async.bulk, tcgen05.mma kind::tf32 (1 or 3 terms), result read back with tcgen05.ld.
-// Exposed as flowmc_debug_tc_gemm so tests/test_gpu_tc.py can check the operand conventions the flow kernels rely on.
+// Exposed as flowmc_test_tc_gemm so tests/test_gpu_tc.py can check the operand conventions the flow kernels rely on.
+// TEST SCAFFOLDING: built into flowmc_b200/lib/libflowmc_b200_test.so (flowmc_b200/build.py), not into the product
+// library; declared in include/flowmc_b200_test.h.
 #include <string>
 
-#include "../../include/flowmc_b200.h"
-#include "registry.h"
-#include "tc_common.cuh"
+#include "../../../include/flowmc_b200_test.h"
+#include "../registry.h"
+#include "../tc_common.cuh"
 
 namespace flowmc {
 
@@ -220,18 +222,18 @@ __global__ void __launch_bounds__(160) tc_gemm_pair_test_kernel(const float* __r
 extern "C" {
 
 // scratch: device, >= ceil(K/32) * 2 * N * 128 bytes
-int flowmc_debug_tc_gemm(const float* A, const float* W, int N, int K, int terms, float* out, float* scratch,
+int flowmc_test_tc_gemm(const float* A, const float* W, int N, int K, int terms, float* out, float* scratch,
                          void* stream_) {
   using namespace flowmc;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!A || !W || !out || !scratch || N < 16 || N > 256 || (N % 16) || K < 32 || K > 128 || (K % 32) ||
       (terms != 1 && terms != 3)) {
-    flowmc_set_error("debug_tc_gemm: need N % 16 == 0 (16..256), K % 32 == 0 (32..128), terms in {1, 3}");
+    flowmc_set_error("test_tc_gemm: need N % 16 == 0 (16..256), K % 32 == 0 (32..128), terms in {1, 3}");
     return FLOWMC_ERR_INVALID;
   }
   const size_t smem = (size_t)(K / 32) * 2 * N * 128;
   if (smem > 200 * 1024) {
-    flowmc_set_error("debug_tc_gemm: stages do not fit shared memory");
+    flowmc_set_error("test_tc_gemm: stages do not fit shared memory");
     return FLOWMC_ERR_UNSUPPORTED;
   }
   tc_pack_b_kernel<<<64, 256, 0, stream>>>(W, N, K, N, scratch);
@@ -248,13 +250,13 @@ int flowmc_debug_tc_gemm(const float* A, const float* W, int N, int K, int terms
 }
 
 // out[256, N] = A[256, K] W[N, K]^T on a CTA pair (cta_group::2).  scratch as above.
-int flowmc_debug_tc_gemm_pair(const float* A, const float* W, int N, int K, int terms, float* out, float* scratch,
+int flowmc_test_tc_gemm_pair(const float* A, const float* W, int N, int K, int terms, float* out, float* scratch,
                               void* stream_) {
   using namespace flowmc;
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!A || !W || !out || !scratch || N < 32 || N > 256 || (N % 16) || K < 32 || K > 128 || (K % 32) ||
       (terms != 1 && terms != 3)) {
-    flowmc_set_error("debug_tc_gemm_pair: need N % 16 == 0 (32..256), K % 32 == 0 (32..128), terms in {1, 3}");
+    flowmc_set_error("test_tc_gemm_pair: need N % 16 == 0 (32..256), K % 32 == 0 (32..128), terms in {1, 3}");
     return FLOWMC_ERR_INVALID;
   }
   const size_t smem = (size_t)(K / 32) * N * 128;   // per CTA: half of every stage

@@ -289,6 +289,13 @@ int flowmc_data_mean_cov(const float* x, int64_t n, int d, float* mean, float* c
   flowmc_count_launch();
   blocks = (n + 31) / 32;
   if (blocks > 148 * 4) blocks = 148 * 4;
+  if (32 * d * sizeof(float) > 48 * 1024) {  // d > 384: beyond the default dynamic shared-memory limit
+    static bool opted_in = false;
+    if (!opted_in) {
+      cudaFuncSetAttribute(cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 512 * (int)sizeof(float));
+      opted_in = true;
+    }
+  }
   cov_kernel<<<(unsigned)blocks, 256, 32 * d * sizeof(float), stream>>>(x, n, d, scratch, cov);
   flowmc_count_launch();
   finish_mean_kernel<<<(unsigned)((d + 63) / 64), 64, 0, stream>>>(scratch, d, 1.0f / (float)n, mean);

@@ -104,9 +104,9 @@ typedef struct FlowmcLocalParams {
   const float* beta;      /* FLOWMC_KERNEL_MALA_TEMPERED: device [n_chains] inverse temperatures 1 / T (NULL = 1) */
   const float* prior;     /* FLOWMC_KERNEL_MALA_TEMPERED: device [4, d] = c, m, lo, hi of
                            * log_prior(x) = -sum_j c_j (x_j - m_j)^2 inside [lo, hi], -inf outside; NULL = flat 0 */
-  int force_n_seg;        /* time slicing: 0 = automatic (slice when there are more chain groups than resident CTA
-                           * slots); > 1 = cut the n_steps into this many segments regardless; < 0 = never slice.
-                           * Results do not depend on it (tests/test_gpu_local_sliced.py) */
+  int force_n_seg;        /* time slicing: <= 0 = one launch for the whole call (default: measured fastest on B200,
+                           * profiles/r02_slice_sweep.jsonl); > 1 = cut the n_steps into this many segments that run
+                           * as successive resident waves.  Results do not depend on it (tests/test_gpu_local_sliced.py) */
   int slots_override;     /* 0 = the device's resident CTA slots; > 0 = plan the rounds as if there were this many
                            * (test hook: forces multi-round launches with a handful of chains) */
 } FlowmcLocalParams;
@@ -120,8 +120,8 @@ FLOWMC_API int64_t flowmc_local_steps_workspace_bytes(int64_t n_chains, int d, i
 FLOWMC_API int flowmc_local_steps_plan(int kind, int target_id, int64_t n_chains, int d, int n_steps,
                                        const FlowmcLocalParams* params, int plan[12]);
 
-/* Runs n_steps of one local kernel for n_chains chains in ONE persistent kernel launch (or, when there are more
- * chain groups than resident CTA slots, one launch per resident wave of (time segment, chain group) work items) and
+/* Runs n_steps of one local kernel for n_chains chains in ONE persistent kernel launch (or, with
+ * params->force_n_seg > 1, one launch per resident wave of (time segment, chain group) work items) and
  * writes the thinned samples straight into the (chain-major) sampler buffers at `cursor`:
  *   pos_buf  device [n_chains, n_total, d]      lp_buf, acc_buf  device [n_chains, n_total]
  * key:      host, the strategy-level rng_key; key_out: host, the rng_key the strategy returns.
@@ -276,22 +276,12 @@ FLOWMC_API int flowmc_adam_optimize(int target_id, const float* target_data, con
                                     int64_t chain_offset, int64_t n_chains_global, uint32_t key_out[2], float* x_out,
                                     float* logp_out, void* stream);
 
-/* ---- diagnostics ---------------------------------------------------------------------------------------- */
-/* out[128, N] = A[128, K] W[N, K]^T through the tcgen05 path (A in TMEM, W as packed swizzled stages, kind::tf32,
- * terms = 1: plain TF32, 3: 3xTF32).  Unit-test hook for the operand conventions of the tensor-core flow kernels.
- * N % 16 == 0 (16..256), K % 32 == 0 (32..128); scratch: device, >= (K/32) * 2 * N * 128 bytes. */
-FLOWMC_API int flowmc_debug_tc_gemm(const float* A, const float* W, int N, int K, int terms, float* out,
-                                    float* scratch, void* stream);
-/* out[256, N] = A[256, K] W[N, K]^T on a CTA pair: one 2-CTA cluster, tcgen05.mma.cta_group::2 with M = 256, each
- * CTA holding 128 rows of A / D in its tensor memory and half of W's rows in its shared memory.  Same limits
- * (N >= 32), same scratch. */
-FLOWMC_API int flowmc_debug_tc_gemm_pair(const float* A, const float* W, int N, int K, int terms, float* out,
-                                         float* scratch, void* stream);
-
-/* diagnostics: CTA 0 of subsequent tensor-core flow launches stamps clock64() at its pipeline events into buf
- * (device, 4 * 256 int64: weight producer / MMA issuer / epilogue thread 0 of the forward kernel, epilogue thread 0
- * of the tensor-core backward kernel); NULL switches it off */
-FLOWMC_API void flowmc_debug_tc_timing(long long* buf);
+/* ---- tracing ---------------------------------------------------------------------------------------------- */
+/* pipeline timeline of the tensor-core flow kernels (the reference's only tracing is its trace-time "Compiling ..."
+ * prints): CTA 0 of subsequent launches stamps clock64() at its pipeline events into buf (device,
+ * 4 * 256 int64: weight producer / MMA issuer / epilogue thread 0 of the forward kernel, epilogue thread 0 of the
+ * tensor-core backward kernel); NULL switches it off.  scripts/tc_timeline.py and scripts/bt_timeline.py print it. */
+FLOWMC_API void flowmc_trace_tc_timeline(long long* buf);
 
 /* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
 FLOWMC_API int64_t flowmc_launch_count(void);

@@ -11,10 +11,10 @@ m = MaskedCouplingRQSpline(d, L, [128, 128], 8, frandom.PRNGKey(1))
 x = frandom.normal(frandom.PRNGKey(2), (16384, d))
 m.loss_and_grad(x)
 buf = torch.zeros(4 * 256, dtype=torch.int64, device="cuda")
-lib.flowmc_debug_tc_timing(buf.data_ptr())
+lib.flowmc_trace_tc_timeline(buf.data_ptr())
 m.loss_and_grad(x)
 torch.cuda.synchronize()
-lib.flowmc_debug_tc_timing(None)
+lib.flowmc_trace_tc_timeline(None)
 t = buf.cpu().numpy().reshape(4, 256)[3]
 v = t[t > 0]
 v = v - v[0]

@@ -16,10 +16,10 @@ x = frandom.normal(frandom.PRNGKey(2), ((128 if train else 148) * 128, d))
 run = (lambda: m.loss_and_grad(x)) if train else (lambda: m.log_prob(x))
 run()
 buf = torch.zeros(4 * 256, dtype=torch.int64, device="cuda")
-lib.flowmc_debug_tc_timing(buf.data_ptr())
+lib.flowmc_trace_tc_timeline(buf.data_ptr())
 run()
 torch.cuda.synchronize()
-lib.flowmc_debug_tc_timing(None)
+lib.flowmc_trace_tc_timeline(None)
 t = buf.cpu().numpy().reshape(4, 256)[:3]
 t0 = t[t > 0].min()
 for role, name in enumerate(("producer (stage slot free -> copy issued)", "mma (ready | first stage | issued)",

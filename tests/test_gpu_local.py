@@ -259,6 +259,33 @@ def test_kernel_call_matches_oracle_step(cuda):
         assert_close(l.cpu().numpy()[same], ol[same], repr(k) + " lp")
 
 
+def test_mala_kernel_ignores_the_incoming_log_prob(cuda):
+    """MALA.kernel recomputes logpdf(position) and never reads its log_prob argument (MALA.py:59,75,87); HMC and GRW
+    do use it (HMC.py:137, Gaussian_random_walk.py:56).  A stale / wrong log_prob must therefore change nothing for
+    MALA -- neither the accept decision nor the value returned on rejection -- and must matter for the other two."""
+    from flowmc_b200 import random as frandom
+    from flowmc_b200 import targets as T
+    from flowmc_b200.resource.logPDF import LogPDF
+    MALA, HMC, GRW = _kernels()
+    d, n = 5, 256
+    logpdf = LogPDF(T.dual_moon(), n_dims=d)
+    keys = frandom.split(frandom.PRNGKey(8), n)
+    x0 = frandom.normal(frandom.PRNGKey(9), (n, d))
+    lp0 = logpdf(x0, None)
+    wrong = lp0 + 7.5
+    k = MALA(0.3)
+    p1, l1, a1 = k.kernel(keys, x0, lp0, logpdf, None)
+    p2, l2, a2 = k.kernel(keys, x0, wrong, logpdf, None)
+    assert torch.equal(p1, p2) and torch.equal(l1, l2) and torch.equal(a1, a2)
+    assert 0 < int(a1.sum()) < n                      # both branches of the where() are exercised
+    assert torch.equal(l1[~a1], lp0[~a1])             # rejected chains return the FRESH logpdf(position)
+    for k in (GRW(0.3), HMC(np.eye(d, dtype=np.float32), 0.05, 4)):
+        _, l1, a1 = k.kernel(keys, x0, lp0, logpdf, None)
+        _, l2, a2 = k.kernel(keys, x0, wrong, logpdf, None)
+        assert torch.equal(l2[~a2], wrong[~a2]), repr(k)   # the incoming value is what a rejection returns
+        assert int(a2.sum()) < int(a1.sum()), repr(k)      # ... and it enters the accept ratio
+
+
 def test_stationarity_unit_gaussian(cuda):
     """test/unit/test_kernels.py:135-184,241-288,344-392: mean ~ 0, var ~ 1 within 3e-2 -- run as
     2048 chains x 2000 steps (the reference runs one chain x 30k-50k steps)."""

@@ -1,7 +1,7 @@
-"""The time-sliced launch path of the persistent local-step kernel (csrc/local_steps.cuh: more chain groups than
-resident CTA slots -> the step range is cut into segments that run as successive launches, chain state handed over
-through a workspace).  Every BASELINE.json local config (C2 8192x1000, C3 32768x200, C5-local 65536x50) and bench.py
-take this path.
+"""The BASELINE.json local configs at full scale, and the time-sliced launch path of the persistent local-step kernel
+(csrc/local_steps.cuh: the step range cut into segments that run as successive launches, chain state handed over
+through a workspace; opt-in through FlowmcLocalParams.force_n_seg since the r02 sweep showed the one-launch grid is
+faster on B200).  C2 8192x1000, C3 32768x200 and C5-local 65536x50 are checked on BOTH launch plans.
 
  * small shapes, slicing FORCED through FlowmcLocalParams.force_n_seg / slots_override: bit-identity with the
    unsliced launch for every kernel kind and lane layout, with n_steps not a multiple of the segment length or of the
@@ -163,16 +163,21 @@ def _baseline_case(name):
     raise KeyError(name)
 
 
+@pytest.mark.parametrize("n_seg", [0, 4], ids=["one-launch", "sliced-x4"])
 @pytest.mark.parametrize("name", ["C2", "C3", "C5-local"])
-def test_baseline_config_against_c_port(cuda, name):
+def test_baseline_config_against_c_port(cuda, name, n_seg):
+    """n_seg = 0: the default plan (what bench.py and the Sampler run); 4: four time segments in resident waves."""
     from flowmc_b200 import random as frandom
     from oracle import cref
     c = _baseline_case(name)
     d, n, T_ = c["d"], c["n"], c["T"]
+    c["kernel"].force_n_seg = n_seg
     plan = _plan(c["kernel"], c["target"], n, d, T_)
     assert plan["n_groups"] > plan["slots"], f"{name}: expected more chain groups than resident slots, got {plan}"
-    if T_ >= 64:
-        assert plan["n_seg"] > 1 and plan["n_rounds"] > 1, f"{name} should take the time-sliced path: {plan}"
+    if n_seg > 1:
+        assert plan["n_seg"] == n_seg and plan["n_rounds"] > n_seg and plan["round_size"] == plan["slots"], plan
+    else:
+        assert plan["n_seg"] == 1 and plan["n_rounds"] == 1, plan
     key = frandom.PRNGKey(1)
     x0 = frandom.normal(frandom.split(frandom.PRNGKey(0))[1], (n, d))
     new_key, res, last, _ = _run_gpu(c["kernel"], c["target"], None, d, key, x0, T_)

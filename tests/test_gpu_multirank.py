@@ -90,6 +90,10 @@ def _worker(rank, world, port, ret):
         assert tf.shape == tp.shape == (cfg["n_max_examples"], dd)
         # the LAST TrainModel call sees buffers produced after a trained flow (DP and single-process flows differ in the
         # last bits, which can flip a global accept): the assembly is compared bit-exactly on identical buffers instead
+        # (not the sampler's own buffer: data_mean / data_cov are accumulated with float atomics, so two PROCESSES
+        # running the same single-GPU sampler agree only to the last bits, and a flipped global accept changes rows)
+        pf = frandom.normal(frandom.PRNGKey(21), (n_chains, 24, dd), device=dev)
+        pf[:, 20:] = float("-inf")                  # unfilled tail of the buffer: skipped by the finite-row filter
         trainer = part.strategies["model_trainer"]
         saved = (trainer.chain_shard, trainer.shard)
         _, sel_part = trainer.select_training_data(frandom.PRNGKey(11), sh.slab(pf).contiguous())

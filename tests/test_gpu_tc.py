@@ -10,14 +10,15 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("N,K", [(128, 32), (128, 128), (16, 32), (112, 64), (208, 96), (256, 64)])
 @pytest.mark.parametrize("terms", [1, 3])
 def test_tc_gemm(cuda, N, K, terms):
-    from flowmc_b200._lib import check, lib
+    from flowmc_b200._lib import check, load_test_lib
+    lib = load_test_lib()
     r = np.random.default_rng(N * 1000 + K)
     A = r.standard_normal((128, K)).astype(np.float32)
     W = (r.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
     Ad, Wd = torch.from_numpy(A).cuda(), torch.from_numpy(W).cuda()
     out = torch.full((128, N), float("nan"), device="cuda")
     scratch = torch.zeros((K // 32) * 2 * N * 32, device="cuda")
-    check(lib.flowmc_debug_tc_gemm(Ad.data_ptr(), Wd.data_ptr(), N, K, terms, out.data_ptr(), scratch.data_ptr(),
+    check(lib.flowmc_test_tc_gemm(Ad.data_ptr(), Wd.data_ptr(), N, K, terms, out.data_ptr(), scratch.data_ptr(),
                                    torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     ref = A.astype(np.float64) @ W.astype(np.float64).T
@@ -33,14 +34,15 @@ def test_tc_gemm(cuda, N, K, terms):
 @pytest.mark.parametrize("terms", [1, 3])
 def test_tc_gemm_cta_pair(cuda, N, K, terms):
     """cta_group::2: a 256 x N x K product on two SMs, each streaming half of W."""
-    from flowmc_b200._lib import check, lib
+    from flowmc_b200._lib import check, load_test_lib
+    lib = load_test_lib()
     r = np.random.default_rng(N * 1000 + K + 7)
     A = r.standard_normal((256, K)).astype(np.float32)
     W = (r.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
     Ad, Wd = torch.from_numpy(A).cuda(), torch.from_numpy(W).cuda()
     out = torch.full((256, N), float("nan"), device="cuda")
     scratch = torch.zeros((K // 32) * 2 * N * 32, device="cuda")
-    check(lib.flowmc_debug_tc_gemm_pair(Ad.data_ptr(), Wd.data_ptr(), N, K, terms, out.data_ptr(), scratch.data_ptr(),
+    check(lib.flowmc_test_tc_gemm_pair(Ad.data_ptr(), Wd.data_ptr(), N, K, terms, out.data_ptr(), scratch.data_ptr(),
                                         torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     ref = A.astype(np.float64) @ W.astype(np.float64).T

@@ -30,6 +30,8 @@ GRAD_CASES = [
     (3, 2, [17, 9], 4, 33),
     (2, 2, [16], 16, 64),
     (7, 2, [8, 8, 8], 8, 200),
+    (32, 10, [128, 128], 8, 260),     # the C4 flow (BASELINE.json configs[3]): depth 10
+    (64, 8, [128, 128], 8, 200),      # the C5 flow (configs[4]): depth 8, d = 64
 ]
 
 
@@ -136,7 +138,7 @@ def test_choice_is_bit_exact(cuda, pop, m):
     assert np.array_equal(out.cpu().numpy(), rng.choice_with_replacement(key, pop, m))
 
 
-@pytest.mark.parametrize("n,d", [(1000, 5), (4097, 64), (300, 3), (50, 130)])
+@pytest.mark.parametrize("n,d", [(1000, 5), (4097, 64), (300, 3), (50, 130), (700, 400), (600, 512)])
 def test_mean_cov(cuda, n, d):
     import ctypes as C
     from flowmc_b200._lib import check, lib
@@ -191,7 +193,7 @@ def test_train_matches_oracle_for_a_few_steps(cuda):
     assert_close(losses.cpu().numpy(), o_losses, "epoch losses", rtol=2e-4)
     q = params_from_model(best)
     for i in range(len(p.W)):
-        assert_close(q.W[i], o_best.W[i], f"W[{i}] after training", rtol=2e-3)
+        assert_close(q.W[i], o_best.W[i], f"W[{i}] after training", rtol=5e-4)
     assert_close(q.data_mean, o_best.data_mean, "data_mean (weight-decayed)", rtol=1e-4)
     assert_close(q.data_cov, o_best.data_cov, "data_cov", rtol=1e-3)
     assert best_state.count == o_state.count == 6
