@@ -50,6 +50,17 @@ class FlowDesc(C.Structure):
     ]
 
 
+class RealNVPDesc(C.Structure):
+    _fields_ = [
+        ("n_features", C.c_int), ("n_layers", C.c_int), ("n_hidden", C.c_int), ("dt", C.c_float),
+        ("off_W1s", C.c_int64), ("off_b1s", C.c_int64), ("off_W2s", C.c_int64), ("off_b2s", C.c_int64),
+        ("off_W1t", C.c_int64), ("off_b1t", C.c_int64), ("off_W2t", C.c_int64), ("off_b2t", C.c_int64),
+        ("off_mask", C.c_int64), ("layer_stride", C.c_int64),
+        ("off_data_mean", C.c_int64), ("off_data_cov", C.c_int64), ("off_base_mean", C.c_int64),
+        ("off_base_cov", C.c_int64), ("n_params", C.c_int64),
+    ]
+
+
 class GlobalParams(C.Structure):
     _fields_ = [
         ("n_batch_size", C.c_int),
@@ -106,6 +117,14 @@ def _load() -> C.CDLL:
         "flowmc_gather_training_rows": (i32, [vp, vp, i64, i32, i32, i32, i64, i64, vp, i64, vp, vp]),
         "flowmc_data_mean_cov": (i32, [vp, i64, i32, vp, vp, vp, vp]),
         "flowmc_trace_tc_timeline": (None, [vp]),
+        "flowmc_realnvp_desc_init": (i32, [C.POINTER(RealNVPDesc), i32, i32, i32, f32]),
+        "flowmc_realnvp_forward": (i32, [C.POINTER(RealNVPDesc), vp, vp, i64, vp, vp, vp]),
+        "flowmc_realnvp_inverse": (i32, [C.POINTER(RealNVPDesc), vp, vp, i64, vp, vp, vp]),
+        "flowmc_realnvp_log_prob": (i32, [C.POINTER(RealNVPDesc), vp, vp, i64, vp, vp]),
+        "flowmc_realnvp_sample": (i32, [C.POINTER(RealNVPDesc), vp, vp, u32p, i64, i64, vp, vp]),
+        "flowmc_realnvp_loss_grad_workspace_bytes": (i64, [C.POINTER(RealNVPDesc), i64]),
+        "flowmc_realnvp_loss_grad": (i32, [C.POINTER(RealNVPDesc), vp, vp, vp, i64, f32, vp, vp, vp, i64, vp]),
+        "flowmc_nf_accept_scan": (i32, [vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp]),
         "flowmc_nf_global_steps_workspace_bytes": (i64, [i64, i32, i32]),
         "flowmc_nf_global_steps": (i32, [C.POINTER(FlowDesc), vp, i32, vp, u32p, vp, vp, vp, vp, i64, i64, i64, i32,
                                          i32, i64, i64, C.POINTER(GlobalParams), u32p, vp, vp]),

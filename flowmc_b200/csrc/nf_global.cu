@@ -278,4 +278,46 @@ int flowmc_nf_global_steps(const FlowmcFlowDesc* D, const float* params, int tar
   return FLOWMC_OK;
 }
 
+int flowmc_nf_accept_scan(const uint32_t* chain_keys, int64_t n_chains, int d, int n_steps, int thinning,
+                          const float* x0, const float* lp0, const float* lp_nf_cur, const float* props,
+                          const float* lp_prop, const float* lp_nf_prop, float* pos_buf, float* lp_buf, float* acc_buf,
+                          int64_t n_total, int64_t cursor, float* last_pos, void* stream_) {
+  using namespace flowmc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_chains < 0 || d < 1 || n_steps < 0 || thinning <= 0) {
+    flowmc_set_error("nf_accept_scan: bad sizes");
+    return FLOWMC_ERR_INVALID;
+  }
+  const int64_t n_out = (n_steps + thinning - 1) / thinning;
+  if (cursor < 0 || cursor + n_out > n_total) {
+    flowmc_set_error("nf_accept_scan: cursor + n_steps/thinning exceeds the buffer length");
+    return FLOWMC_ERR_INVALID;
+  }
+  if (n_chains == 0 || n_steps == 0) return FLOWMC_OK;
+  if (!chain_keys || !x0 || !lp0 || !lp_nf_cur || !props || !lp_prop || !lp_nf_prop || !pos_buf || !lp_buf ||
+      !acc_buf || !last_pos) {
+    flowmc_set_error("nf_accept_scan: null buffer");
+    return FLOWMC_ERR_INVALID;
+  }
+  NfArgs a;
+  a.subkey = Key{0, 0};
+  a.chain_keys = chain_keys;
+  a.chain_offset = 0;
+  a.n_chains = n_chains;
+  a.n_steps = n_steps;
+  a.n_batch = 0;
+  a.n_sample = n_steps;
+  const int wpb = 4;
+  nf_accept_kernel<<<(unsigned)((n_chains + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+      a, d, x0, lp0, lp_nf_cur, props, lp_prop, lp_nf_prop, thinning, pos_buf, lp_buf, acc_buf, n_total, cursor,
+      last_pos);
+  flowmc_count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    flowmc_set_error(cudaGetErrorString(e));
+    return FLOWMC_ERR_CUDA;
+  }
+  return FLOWMC_OK;
+}
+
 }  // extern "C"

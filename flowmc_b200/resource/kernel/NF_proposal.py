@@ -35,6 +35,49 @@ class NFProposal(ProposalBase):
         self.n_batch_size = n_NFproposal_batch_size
         self._workspace = None
 
+    def _run_generic(self, key, x0, logpdf, data, bufs, n_total, start, n_steps, thinning, offset, n_glob,
+                     chain_keys=None, lp0=None):
+        """Any NFModel with ``log_prob`` and ``sample_rows`` (RealNVP): the passes of NF_proposal.py:27-128 as
+        separate launches -- target and flow log-probs of the current positions, proposals drawn with the
+        reference's per-chain key schedule, their flow and target log-probs, then the sequential accept scan
+        (``flowmc_nf_accept_scan``) writing the thinned samples into the buffers."""
+        from ... import random as frandom
+        pos, lp, acc = bufs
+        n, d = x0.shape
+        dev = x0.device
+        key = np.ascontiguousarray(key, dtype=np.uint32)
+        key_out, subkey = frandom.split(key)                                              # take_steps.py:71
+        if chain_keys is None:
+            ck = frandom.split(subkey, n_glob)[offset:offset + n]                         # take_steps.py:72
+        else:
+            ck = np.ascontiguousarray(chain_keys.cpu().numpy().view(np.uint32).reshape(n, 2))
+        sub = frandom.split_each(ck, 2)[:, 1]                                             # NF_proposal.py:41
+        if n_steps > self.n_batch_size:                                                   # NF_proposal.py:135-163
+            n_batch = -(-n_steps // self.n_batch_size)
+            n_sample = -(-n_steps // n_batch)
+            keys_b = np.zeros((n, n_batch, 2), np.uint32)
+            carry = sub
+            for b in range(n_batch):
+                two = frandom.split_each(carry, 2)
+                carry, keys_b[:, b] = two[:, 0], two[:, 1]
+            keys_d = torch.from_numpy(np.ascontiguousarray(keys_b.reshape(-1, 2)).view(np.int32)).to(dev)
+            props = self.model.sample_rows(keys_d, n_sample).reshape(n, n_batch * n_sample, d)[:, :n_steps].contiguous()
+        else:
+            keys_d = torch.from_numpy(np.ascontiguousarray(sub).view(np.int32)).to(dev)
+            props = self.model.sample_rows(keys_d, n_steps).reshape(n, n_steps, d)
+        lp_nf_cur = self.model.log_prob(x0).contiguous()                                  # NF_proposal.py:44
+        lp_nf_prop = self.model.log_prob(props.reshape(-1, d)).contiguous()               # NF_proposal.py:167
+        lp_prop = logpdf(props.reshape(-1, d), data).contiguous()                         # NF_proposal.py:50-89
+        lp0 = logpdf(x0, data).contiguous() if lp0 is None else lp0                       # take_steps.py:201
+        ck_d = torch.from_numpy(np.ascontiguousarray(ck).view(np.int32)).to(dev)
+        last = torch.empty((n, d), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.flowmc_nf_accept_scan(ck_d.data_ptr(), n, d, n_steps, thinning, x0.data_ptr(), lp0.data_ptr(),
+                                            lp_nf_cur.data_ptr(), props.data_ptr(), lp_prop.data_ptr(),
+                                            lp_nf_prop.data_ptr(), pos.data_ptr(), lp.data_ptr(), acc.data_ptr(),
+                                            n_total, start, last.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return key_out, last
+
     def _run(self, key, x0, logpdf, data, bufs, n_total, start, n_steps, thinning, offset, n_glob,
              chain_keys=None, lp0=None):
         assert isinstance(logpdf, LogPDF), "logpdf resource must be a LogPDF"
@@ -43,6 +86,9 @@ class NFProposal(ProposalBase):
         dev = x0.device
         if d != self.model.n_features:
             raise ValueError(f"flow has {self.model.n_features} features, chains have {d}")
+        if not hasattr(self.model.desc, "num_bins"):      # not the spline flow: no fused proposal kernel
+            return self._run_generic(key, x0, logpdf, data, bufs, n_total, start, n_steps, thinning, offset, n_glob,
+                                     chain_keys, lp0)
         self.model.prepare()
         ws_bytes = int(lib.flowmc_nf_global_steps_workspace_bytes(n, d, n_steps))
         if self._workspace is None or self._workspace.numel() < ws_bytes or self._workspace.device != dev:

@@ -38,8 +38,8 @@ class _TrainScratch:
         d = model.desc
         self.grad = torch.empty(int(d.n_params), dtype=torch.float32, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.ws = torch.empty(max(16, int(lib.flowmc_flow_loss_grad_workspace_bytes(C.byref(d), batch_rows))),
-                              dtype=torch.uint8, device=dev)
+        self.ws = torch.empty(max(16, int(model._loss_grad_workspace_bytes(batch_rows))), dtype=torch.uint8,
+                              device=dev)
         self.perm = torch.empty(max(1, n_rows), dtype=torch.int32, device=dev)
         self.perm_ws = torch.empty(max(16, int(lib.flowmc_random_permutation_workspace_bytes(n_rows))),
                                    dtype=torch.uint8, device=dev)
@@ -87,6 +87,17 @@ class NFModel(Resource):
     dp = None
     dp_min_rows_per_rank = int(os.environ.get("FLOWMC_DP_MIN_ROWS", 0))
 
+    # model-specific C-ABI calls behind loss_and_grad (the spline flow's; RealNVP overrides both)
+    def _loss_grad_workspace_bytes(self, n_rows: int) -> int:
+        return int(lib.flowmc_flow_loss_grad_workspace_bytes(C.byref(self.desc), int(n_rows)))
+
+    def _loss_grad_call(self, x_ptr, idx_ptr, n, inv_n_total, grad_ptr, loss_ptr, ws_ptr, ws_bytes, stream):
+        return lib.flowmc_flow_loss_grad(C.byref(self.desc), self.params.data_ptr(), x_ptr, idx_ptr, n, inv_n_total,
+                                         grad_ptr, loss_ptr, ws_ptr, ws_bytes, stream)
+
+    def prepare(self):
+        """Hook: refresh derived device state after a parameter change (the spline flow's tensor-core image)."""
+
     def loss_and_grad(self, x, idx=None, scratch=None, n_global=None):
         """NFModel.loss_fn (base.py:98-100): (-mean log_prob, flat gradient).  ``idx`` (int32 device
         tensor) selects rows of ``x``."""
@@ -95,10 +106,9 @@ class NFModel(Resource):
         sc = scratch or _TrainScratch(self, 0, n)
         self.prepare()     # refresh the tensor-core weight image: params change every step
         with torch.cuda.device(x.device):
-            check(lib.flowmc_flow_loss_grad(C.byref(self.desc), self.params.data_ptr(), x.data_ptr(),
-                                            idx.data_ptr() if idx is not None else None, n,
-                                            1.0 / float(n_global or n), sc.grad.data_ptr(), sc.loss.data_ptr(),
-                                            sc.ws.data_ptr(), sc.ws.numel(), _stream()))
+            check(self._loss_grad_call(x.data_ptr(), idx.data_ptr() if idx is not None else None, n,
+                                       1.0 / float(n_global or n), sc.grad.data_ptr(), sc.loss.data_ptr(),
+                                       sc.ws.data_ptr(), sc.ws.numel(), _stream()))
         return sc.loss, sc.grad
 
     def _apply_update(self, optim, state, sc):

@@ -231,6 +231,53 @@ FLOWMC_API int flowmc_clip_adamw(int64_t n_params, float* params, const float* g
                                  int64_t count, double lr, double b1, double b2, double eps, double weight_decay,
                                  double max_norm, float* scratch, float* gnorm_out, void* stream);
 
+/* ---- RealNVP (resource/model/nf_model/realNVP.py:102-228) ---------------------------------
+ * n_layers x MaskedCouplingLayer(MLPAffine(scale_MLP, shift_MLP), mask), both MLPs [d, n_hidden, d] with relu
+ * (common.py:68-124 default activation).  ONE flat float32 blob like the spline flow:
+ *   per layer l at l*layer_stride: W1s [h,d], b1s [h], W2s [d,h], b2s [d] (scale MLP), W1t, b1t, W2t, b2t (shift
+ *     MLP), mask [d] -- the reference's coupling mask is a FLOAT leaf (1 = conditioning / unchanged, 0 = transformed)
+ *     that gets zero gradient but AdamW weight decay; the kernels evaluate the layer with the general float mask
+ *   tail: data_mean [d], data_cov [d,d], base mean [d], base cov [d,d]
+ * dt: MLPAffine / AffineCoupling's scaling factor (scale = tanh(.) * dt, shift = (.) * dt; RealNVP uses 1). */
+typedef struct FlowmcRealNVPDesc {
+  int n_features, n_layers, n_hidden;
+  float dt;
+  int64_t off_W1s, off_b1s, off_W2s, off_b2s, off_W1t, off_b1t, off_W2t, off_b2t, off_mask;
+  int64_t layer_stride;
+  int64_t off_data_mean, off_data_cov, off_base_mean, off_base_cov;
+  int64_t n_params;
+} FlowmcRealNVPDesc;
+
+FLOWMC_API int flowmc_realnvp_desc_init(FlowmcRealNVPDesc* desc, int n_features, int n_layers, int n_hidden, float dt);
+/* RealNVP.forward / .inverse (realNVP.py:172-206): x device [n,d] -> y device [n,d], logdet device [n] */
+FLOWMC_API int flowmc_realnvp_forward(const FlowmcRealNVPDesc* desc, const float* params, const float* x, int64_t n,
+                                      float* y, float* logdet, void* stream);
+FLOWMC_API int flowmc_realnvp_inverse(const FlowmcRealNVPDesc* desc, const float* params, const float* x, int64_t n,
+                                      float* y, float* logdet, void* stream);
+/* RealNVP.log_prob (realNVP.py:214-221): whitening, forward, + multivariate_normal.logpdf(y, zeros, eye) */
+FLOWMC_API int flowmc_realnvp_log_prob(const FlowmcRealNVPDesc* desc, const float* params, const float* x, int64_t n,
+                                       float* log_prob, void* stream);
+/* RealNVP.sample (realNVP.py:208-212); keys / host_key / rows_per_key as in flowmc_flow_sample */
+FLOWMC_API int flowmc_realnvp_sample(const FlowmcRealNVPDesc* desc, const float* params, const uint32_t* keys,
+                                     const uint32_t host_key[2], int64_t rows_per_key, int64_t n, float* x_out,
+                                     void* stream);
+/* NFModel.loss_fn + gradient for a RealNVP (same contract as flowmc_flow_loss_grad; the masks and the tail get zero
+ * gradient).  Weight gradients are accumulated with float atomics (not bit-reproducible run to run). */
+FLOWMC_API int64_t flowmc_realnvp_loss_grad_workspace_bytes(const FlowmcRealNVPDesc* desc, int64_t n);
+FLOWMC_API int flowmc_realnvp_loss_grad(const FlowmcRealNVPDesc* desc, const float* params, const float* x,
+                                        const int32_t* idx, int64_t n, float inv_n_total, float* grad, float* loss,
+                                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The sequential accept scan of NFProposal.kernel (NF_proposal.py:91-126) on its own, for proposal models other than
+ * the fused spline path: chain c continues with rng_key = split(chain_keys[c])[0]; per step key, sub = split(key),
+ * accept when log(uniform(sub)) < (lp_prop - lp) - (lp_nf_prop - lp_nf).  chain_keys device [n_chains,2]; x0 device
+ * [n_chains,d]; lp0, lp_nf_cur device [n_chains]; props device [n_chains,n_steps,d]; lp_prop, lp_nf_prop device
+ * [n_chains,n_steps]; thinned results go into the sampler buffers at `cursor` as in flowmc_nf_global_steps. */
+FLOWMC_API int flowmc_nf_accept_scan(const uint32_t* chain_keys, int64_t n_chains, int d, int n_steps, int thinning,
+                                     const float* x0, const float* lp0, const float* lp_nf_cur, const float* props,
+                                     const float* lp_prop, const float* lp_nf_prop, float* pos_buf, float* lp_buf,
+                                     float* acc_buf, int64_t n_total, int64_t cursor, float* last_pos, void* stream);
+
 /* ---- training-set plumbing (strategy/train_model.py:66-81, nf_model/base.py:141-144,187-188) --------------- */
 /* jax.random.permutation(key, n) -> out device int32[n] */
 FLOWMC_API int64_t flowmc_random_permutation_workspace_bytes(int64_t n);

@@ -19,6 +19,7 @@ import numpy as np
 import torch
 
 from . import flow as oflow
+from . import realnvp as orealnvp
 from . import rng
 from .targets import TARGETS
 
@@ -26,6 +27,13 @@ F32 = np.float32
 
 
 # ------------------------------------------------------------------------------ NFProposal
+def _model_log_prob(p, x):
+    """model.log_prob for either flow family (FlowParams: spline flow, NVPParams: RealNVP)."""
+    if isinstance(p, orealnvp.NVPParams):
+        return orealnvp.log_prob(p, x)
+    return oflow.log_prob(p, x)
+
+
 def sample_flow(p, keys, n_steps, n_batch_size):
     """NF_proposal.py:130-172 for a batch of per-chain keys [n,2] -> (positions [n,S,d], flow log-probs [n,S])."""
     n = keys.shape[0]
@@ -41,18 +49,20 @@ def sample_flow(p, keys, n_steps, n_batch_size):
             z = rng.normal(sub, (n_sample, d))                       # [n, n_sample, d]
             x = _sample_from_z(p, z.reshape(-1, d))
             pos.append(x.reshape(n, n_sample, d))
-            lps.append(oflow.log_prob(p, x).reshape(n, n_sample))
+            lps.append(_model_log_prob(p, x).reshape(n, n_sample))
         pos = np.concatenate(pos, axis=1)[:, :n_steps]
         lps = np.concatenate(lps, axis=1)[:, :n_steps]
     else:
         z = rng.normal(keys, (n_steps, d))
         x = _sample_from_z(p, z.reshape(-1, d))
         pos = x.reshape(n, n_steps, d)
-        lps = oflow.log_prob(p, x).reshape(n, n_steps)
+        lps = _model_log_prob(p, x).reshape(n, n_steps)
     return pos.astype(F32), lps.astype(F32)
 
 
 def _sample_from_z(p, z):
+    if isinstance(p, orealnvp.NVPParams):
+        return orealnvp.sample_from_z(p, z)
     L = np.linalg.cholesky(p.base_cov.astype(np.float64)).astype(F32)
     z = (p.base_mean + z @ L.T).astype(F32)
     x, _ = oflow.inverse(p, z)
@@ -65,7 +75,7 @@ def nf_proposal_kernel(p, keys, position, log_prob, target, data, n_steps, n_bat
     n, d = position.shape
     s = rng.split(keys, 2)
     rk, sub = s[:, 0], s[:, 1]
-    lp_nf_cur = oflow.log_prob(p, position)
+    lp_nf_cur = _model_log_prob(p, position)
     prop, lp_nf_prop = sample_flow(p, sub, n_steps, n_batch_size)
     lp_prop = tgt.logp_grad(prop.reshape(-1, d), data)[0].reshape(n, n_steps)
     x = position.astype(F32).copy()

@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from oracle import flow as oflow, local as olocal, nf, optimization as oopt  # noqa: E402
-from oracle import parallel_tempering as opt_pt, rng, targets as otargets  # noqa: E402
+from oracle import parallel_tempering as opt_pt, realnvp as onvp, rng, targets as otargets  # noqa: E402
 from flowutil import random_params  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
@@ -110,8 +110,53 @@ def strategies_case():
                         pt_temperatures=pt_t, pt_accepts=pt_acc)
 
 
+def realnvp_params(seed, d, L, h, gain=30.0):
+    """RealNVP parameters away from the near-identity initialisation (first-layer weights are drawn with
+    std sqrt(1e-4 / d)): scaled-up first layers, non-trivial whitening constants, and masks part-way through the
+    weight-decay shrinkage the reference applies to them (1 -> 0.97)."""
+    r = np.random.default_rng(seed)
+    p = onvp.init_params(rng.PRNGKey(seed), d, L, h)
+    p.W1 = (p.W1 * np.float32(gain)).astype(np.float32)
+    p.mask = (p.mask * np.float32(0.97)).astype(np.float32)
+    p.data_mean = r.standard_normal(d).astype(np.float32)
+    a = r.standard_normal((d, d)) * 0.3
+    p.data_cov = (a @ a.T + np.diag(0.5 + r.random(d))).astype(np.float32)
+    p.base_cov = (p.base_cov * np.float32(0.98)).astype(np.float32)
+    return p
+
+
+def realnvp_case():
+    """RealNVP: bijection, log_prob, sample, loss gradient, bit-level initialisation and two
+    NFProposal runs, on the shapes of test/unit/test_nf.py:24-52 and a wider one."""
+    d, L, h, n = 5, 4, 16, 24
+    p = realnvp_params(31, d, L, h)
+    x = (2.0 * np.random.default_rng(3).standard_normal((n, d))).astype(np.float32)
+    y, ld = onvp.forward(p, x)
+    xi, ldi = onvp.inverse(p, x)
+    key = rng.PRNGKey(123)
+    loss, g = onvp.loss_and_grads(p, x)
+    blob = dict(x=x, fwd_y=y, fwd_logdet=ld, inv_x=xi, inv_logdet=ldi, log_prob=onvp.log_prob(p, x), sample_key=key,
+                sample=onvp.sample(p, key, 16), params_flat=onvp.flatten(p), shape=np.array([d, L, h], np.int32),
+                loss=np.float32(loss), grad_flat=onvp.flatten(g, p))
+    p0 = onvp.init_params(rng.PRNGKey(0), 3, 2, 4)          # test_nf.py:30-31 builds RealNVP(3, 2, 4, key)
+    blob.update(init_key0_flat=onvp.flatten(p0),
+                init_key0_log_prob=onvp.log_prob(p0, np.array([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]], np.float32)))
+    ks = rng.split(rng.PRNGKey(7), 2)
+    x0 = rng.normal(ks[1], (6, d))
+    packed = otargets.IsoGaussian.pack(d, 0.5)
+    for tag, bs in (("simple", 100), ("batched", 3)):
+        nk, pos, lp, acc, last, dbg = nf.take_group_steps(ks[0], x0, p, "iso_gaussian", packed, 7, bs)
+        blob.update({f"nf_{tag}_key": nk, f"nf_{tag}_pos": pos, f"nf_{tag}_lp": lp, f"nf_{tag}_acc": acc,
+                     f"nf_{tag}_proposals": dbg["proposals"], f"nf_{tag}_lp_nf": dbg["lp_nf_prop"]})
+    blob.update(nf_key=ks[0], nf_x0=x0)
+    np.savez_compressed(os.path.join(OUT, "realnvp_d5.npz"), **blob)
+
+
 if __name__ == "__main__":
-    flow_case(); init_case(); local_case(); nf_case(); rng_case(); strategies_case()
+    which = sys.argv[1:] or ["flow", "init", "local", "nf", "rng", "strategies", "realnvp"]
+    for name in which:
+        {"flow": flow_case, "init": init_case, "local": local_case, "nf": nf_case, "rng": rng_case,
+         "strategies": strategies_case, "realnvp": realnvp_case}[name]()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))
