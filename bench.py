@@ -167,6 +167,43 @@ def cpu_reference_rate(target_seconds: float = 12.0):
     return n * steps / dt, threads, steps, dt
 
 
+def tf32_peak(dev, n=8192, burst_iters=10, sustained_s=2.0):
+    """Measured TF32 tensor-core peak of this GPU: cuBLAS fp32 GEMM with TF32 allowed (torch.matmul, n^3), best single
+    launch (burst) and a seconds-long back-to-back loop (sustained), as MEASURED_PEAKS.json does for bf16.  The
+    denominator for the flow kernels' TF32 fractions (BASELINE.md section 2 asks for a measured figure)."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn((n, n), device=dev, dtype=torch.float32)
+        b = torch.randn((n, n), device=dev, dtype=torch.float32)
+        c = torch.empty((n, n), device=dev, dtype=torch.float32)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(burst_iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        iters = max(4, int(sustained_s * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        sus = e0.elapsed_time(e1) / iters
+        fl = 2.0 * n ** 3
+        return {"burst_tflops": fl / best / 1e9, "sustained_tflops": fl / sus / 1e9,
+                "how": f"torch.matmul fp32 {n}^3 with allow_tf32 (cuBLAS TF32), best of {burst_iters} / {iters} back to back"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def flow_extras(dev):
     """Device-timed measurements of the flow kernels at the BASELINE.json shapes (C4 training batch, C5 global
     steps); reported under "extra" next to the headline local-step metric."""
@@ -185,6 +222,11 @@ def flow_extras(dev):
 
     nc = ncu_constants()
     out = {}
+    try:
+        out["tf32_peak_measured"] = tf32_peak(dev)
+    except Exception as ex:
+        out["tf32_peak_measured"] = {"error": repr(ex)}
+    tf32_burst = out["tf32_peak_measured"].get("burst_tflops")
     # C4 flow: 32-D, 10 layers, [128,128], 8 bins
     m = MaskedCouplingRQSpline(32, 10, [128, 128], 8, frandom.PRNGKey(1), device=dev)
     n = 148 * 128 * 4
@@ -201,6 +243,8 @@ def flow_extras(dev):
         "path": f"tcgen05 {m.desc.tc_terms}xTF32" if m.desc.tc_terms else "fp32 CUDA cores",
         "issued_tflops": issued * n / ms / 1e9,
         "tensor_pipe_frac_from_rate": issued * n / ms / 1e9 / pipe_peak,
+        "issued_frac_of_measured_tf32_burst": (issued * n / ms / 1e9 / tf32_burst) if tf32_burst else None,
+        "useful_frac_of_measured_tf32_burst": (fl * n / ms / 1e9 / tf32_burst) if tf32_burst else None,
         "tensor_pipe_active_ncu": nc.get("flow_tc_log_prob_c4", {"note": "no committed capture"}),
         "note": "issued = 3 TF32 terms x the padded GEMM shapes; pipe peak = 4096 flop/clk/SM x 148 SMs x 1.965 GHz = "
                 "1191 TFLOP/s (nominal; tensor_pipe_frac_from_rate is computed from THIS run's rate, "
@@ -212,6 +256,7 @@ def flow_extras(dev):
     ms = st["median"]
     out["flow_train_c4"] = {"samples_per_s": bs / ms * 1e3, "batch": bs, "ms_per_step": st,
                             "useful_tflops": 3 * fl * bs / ms / 1e9,
+                            "useful_frac_of_measured_tf32_burst": (3 * fl * bs / ms / 1e9 / tf32_burst) if tf32_burst else None,
                             "note": "training forward (tcgen05, leaves spline parameters + packed activation images) + "
                                     "hand-written backward (tcgen05 dgrad/wgrad, in-kernel deterministic reduction) + "
                                     "fused clip/AdamW; per-kernel split: scripts/prof_train.py"}

@@ -8,6 +8,8 @@ from __future__ import annotations
 
 import torch
 
+from .tracing import nvtx_range
+
 _SETTINGS = {"verbose": False, "logging": True, "outdir": "./outdir/"}   # keyword overrides the reference accepts
 
 
@@ -48,7 +50,8 @@ class Sampler:
         position = torch.atleast_2d(torch.as_tensor(initial_position, dtype=torch.float32))
         key = self.rng_key
         for name in self.strategy_order:
-            key, self.resources, position = self._strategy(name)(key, self.resources, position, data)
+            with nvtx_range(f"flowmc/{name}"):       # one NVTX range per strategy call
+                key, self.resources, position = self._strategy(name)(key, self.resources, position, data)
         self.rng_key, self.last_step = key, position
 
     def serialize(self):

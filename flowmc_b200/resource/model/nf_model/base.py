@@ -22,6 +22,7 @@ import torch
 from .... import random as frandom
 from ...._lib import check, lib
 from ...base import Resource
+from ....tracing import nvtx_range
 
 _u32p = C.POINTER(C.c_uint32)
 
@@ -194,7 +195,8 @@ class NFModel(Resource):
             it = trange(num_epochs, desc="Training NF", miniters=max(1, int(num_epochs / 10)))
         for epoch in it:
             rng, input_rng = frandom.split(rng)
-            value = model.train_epoch(input_rng, optim, state, data, batch_size, sc)
+            with nvtx_range(f"flowmc/train_epoch[{epoch}]"):
+                value = model.train_epoch(input_rng, optim, state, data, batch_size, sc)
             loss_values[epoch] = float(value.item())              # the reference's per-epoch host read
             if loss_values[epoch] < best_loss:
                 if best_model is self:

@@ -29,21 +29,50 @@ class Recorder:
         return out
 
 
-def test_quickstart_bundle_runs_and_every_call_matches_the_oracle(cuda):
+CONFIGS = {
+    # a miniature of the quickstart that reaches the batched branch of sample_flow (n_global > n_NFproposal_batch_size)
+    "small": dict(n_local=20, n_global=5, n_train=2, n_prod=2, n_epochs=2, hidden=[16, 16], n_layers=3, batch_size=128,
+                  n_max_examples=400, nf_batch=3),
+    # C1 = BASELINE.json configs[0] EXACTLY as SURVEY.md 8(d) states it (docs/tutorials/dualmoon.ipynb cells 5, 8, 11):
+    # 5-D dual moon, 20 chains, 100 local + 10 global steps, 20 training + 20 production loops, 5 epochs, lr 5e-3,
+    # batch_size = n_max_examples = 5000, MALA 0.1, flow 4 x [32, 32] x 8 bins, PRNGKey(42) split as in the notebook
+    "C1": dict(n_local=100, n_global=10, n_train=20, n_prod=20, n_epochs=5, hidden=[32, 32], n_layers=4, batch_size=5000,
+               n_max_examples=5000, nf_batch=10000),
+}
+
+
+def _moments_to_oracle(model, flat_dev):
+    """A device-layout flat vector (Adam moment) in the oracle's flat order (no alignment padding)."""
+    from oracle import nf
+    mm = model.clone()
+    mm.params.copy_(torch.from_numpy(np.asarray(flat_dev)).to(mm.params.device))
+    return nf.flatten(params_from_model(mm))
+
+
+@pytest.mark.parametrize("cfg_name", ["small", "C1"])
+def test_quickstart_bundle_runs_and_every_call_matches_the_oracle(cuda, cfg_name):
     from flowmc_b200 import random as frandom, targets as T
     from flowmc_b200.Sampler import Sampler
     from flowmc_b200.resource_strategy_bundle.RQSpline_MALA import RQSpline_MALA_Bundle
     from oracle import local as olocal, nf, rng, targets as otargets
 
+    c = CONFIGS[cfg_name]
     n_chains, d = 20, 5
-    n_local, n_global, n_train, n_prod, n_epochs = 20, 5, 2, 2, 2
+    n_local, n_global, n_train, n_prod, n_epochs = c["n_local"], c["n_global"], c["n_train"], c["n_prod"], c["n_epochs"]
     key = frandom.PRNGKey(42)
-    key, sub = frandom.split(key)
-    x0 = frandom.normal(sub, (n_chains, d))
-    key, sub = frandom.split(key)
-    bundle = RQSpline_MALA_Bundle(sub, n_chains, d, T.dual_moon(), n_local, n_global, n_train, n_prod, n_epochs,
-                                  mala_step_size=0.1, rq_spline_hidden_units=[16, 16], rq_spline_n_layers=3,
-                                  learning_rate=5e-3, batch_size=128, n_max_examples=400, n_NFproposal_batch_size=3)
+    if cfg_name == "C1":      # notebook order: the bundle takes the first sub-key, the initial position the second
+        key, sub = frandom.split(key)
+        bundle_key = sub
+        key, sub = frandom.split(key)
+        x0 = frandom.normal(sub, (n_chains, d)) * 1
+    else:
+        key, sub = frandom.split(key)
+        x0 = frandom.normal(sub, (n_chains, d))
+        key, bundle_key = frandom.split(key)
+    bundle = RQSpline_MALA_Bundle(bundle_key, n_chains, d, T.dual_moon(), n_local, n_global, n_train, n_prod, n_epochs,
+                                  mala_step_size=0.1, rq_spline_hidden_units=c["hidden"], rq_spline_n_bins=8,
+                                  rq_spline_n_layers=c["n_layers"], learning_rate=5e-3, batch_size=c["batch_size"],
+                                  n_max_examples=c["n_max_examples"], n_NFproposal_batch_size=c["nf_batch"])
     assert repr(bundle) == "RQSpline_MALA Bundle"
     assert len(bundle.strategy_order) == 6 * n_train + 2 + 4 * n_prod
 
@@ -65,6 +94,7 @@ def test_quickstart_bundle_runs_and_every_call_matches_the_oracle(cuda):
             s["buf"] = resources["positions_training"].data.cpu().numpy().copy()
             s["count"] = resources["optimizer"].optim_state.count
             s["mu"] = resources["optimizer"].optim_state.mu.cpu().numpy().copy()
+            s["nu"] = resources["optimizer"].optim_state.nu.cpu().numpy().copy()
             s["loss"] = resources["loss_buffer"].data.cpu().numpy().copy()
         return s
 
@@ -104,20 +134,24 @@ def test_quickstart_bundle_runs_and_every_call_matches_the_oracle(cuda):
             assert e["post"]["cursor"] == c0 + n_local
         elif e["name"] == "global_stepper":
             o_key, o_pos, o_lp, o_acc, o_last, dbg = nf.take_group_steps(
-                e["key_in"], e["x_in"], e["pre"]["flow"], "dual_moon", packed, n_global, 3)
+                e["key_in"], e["x_in"], e["pre"]["flow"], "dual_moon", packed, n_global, c["nf_batch"])
             sl = slice(c0, c0 + n_global)
             assert np.array_equal(e["key_out"], o_key)
             compare_chains((e["post"]["pos"][:, sl], e["post"]["lp"][:, sl], e["post"]["acc"][:, sl]),
                            (o_pos, o_lp, o_acc), dbg["steps"], max_diverged_frac=0.1)
         else:
-            k1, tkey, data, idx = nf.select_training_data(e["key_in"], e["pre"]["buf"], 400, 100)
+            k1, tkey, data, idx = nf.select_training_data(e["key_in"], e["pre"]["buf"], c["n_max_examples"], 100)
             ost = nf.AdamWState(nf.flatten(e["pre"]["flow"]).size)
             ost.count = e["pre"]["count"]
             if ost.count:
-                continue     # later trainings start from a warm optimiser state; the first one is checked in full
-            o_key, o_best, o_st, o_losses = nf.train(e["pre"]["flow"], tkey, data, ost, 5e-3, n_epochs, 128)
+                # later trainings start from a warm optimiser state: the oracle gets the GPU run's Adam moments
+                # (device layout = oracle layout + alignment padding; re-pack through the model's views)
+                ost.mu = _moments_to_oracle(sampler.resources["model"], e["pre"]["mu"])
+                ost.nu = _moments_to_oracle(sampler.resources["model"], e["pre"]["nu"])
+            o_key, o_best, o_st, o_losses = nf.train(e["pre"]["flow"], tkey, data, ost, 5e-3, n_epochs, c["batch_size"])
             assert np.array_equal(e["key_out"], o_key)
-            assert_close(e["post"]["loss"][:n_epochs], o_losses, "training losses", rtol=5e-4)
+            k0 = n_checked["model_trainer"] * n_epochs
+            assert_close(e["post"]["loss"][k0:k0 + n_epochs], o_losses, "training losses", rtol=5e-4)
             q = e["post"]["flow"]
             assert_close(q.data_mean, o_best.data_mean, "data_mean", rtol=1e-4)
             for i in range(len(q.W)):
@@ -125,7 +159,11 @@ def test_quickstart_bundle_runs_and_every_call_matches_the_oracle(cuda):
             assert np.array_equal(e["x_in"], e["x_out"])
         n_checked[e["name"]] += 1
     assert n_checked["local_stepper"] == n_train + n_prod and n_checked["global_stepper"] == n_train + n_prod
-    assert n_checked["model_trainer"] >= 1
+    assert n_checked["model_trainer"] == n_train
+    if cfg_name == "C1":      # the flow has learned the two moons by the production phase (dualmoon.ipynb's outcome)
+        ga = res["global_accs_production"].data
+        assert float(ga[torch.isfinite(ga)].mean()) > 0.05
+        assert float(res["loss_buffer"].data[-1]) < float(res["loss_buffer"].data[0])
 
 
 def test_sampler_dual_moon_statistics(cuda):

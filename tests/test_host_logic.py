@@ -56,3 +56,23 @@ def test_adam_optimization_argument_checks_need_no_gpu():
     from flowmc_b200.strategy.optimization import AdamOptimization
     with pytest.raises(TypeError):
         AdamOptimization(lambda x, data: 0.0)
+
+
+def test_nvtx_ranges_wrap_every_strategy_call():
+    """flowmc_b200.tracing: one NVTX range per strategy call of Sampler.sample (no GPU needed: NVTX is a stub unless a
+    profiler is attached)."""
+    from flowmc_b200 import tracing
+    from flowmc_b200.Sampler import Sampler
+    calls = []
+
+    def strat(name):
+        def f(key, resources, x, data):
+            calls.append(name)
+            return key, resources, x
+        return f
+    s = Sampler(2, 1, np.zeros(2, np.uint32), resources={}, strategies={"a": strat("a"), "b": strat("b")},
+                strategy_order=["a", "b", "a"])
+    before = tracing.ranges_opened
+    s.sample(np.zeros((1, 2), np.float32), {})
+    assert calls == ["a", "b", "a"]
+    assert tracing.ranges_opened - before in (0, 3)     # 3 when NVTX is loadable, 0 when tracing is unavailable
