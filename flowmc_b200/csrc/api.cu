@@ -242,7 +242,7 @@ int flowmc_local_steps(int kind, int target_id, const float* target_data, const 
     return fail(FLOWMC_ERR_INVALID, "local_steps: cursor + n_steps/thinning exceeds the buffer length");
   if (params->step_keys && n_steps != 1)
     return fail(FLOWMC_ERR_INVALID, "local_steps: explicit step_keys require n_steps == 1");
-  if (kind == FLOWMC_KERNEL_HMC && (!params->hmc_chol || !params->hmc_colsum || params->n_leapfrog < 0))
+  if ((kind == FLOWMC_KERNEL_HMC || kind == FLOWMC_KERNEL_HMC_TEMPERED) && (!params->hmc_chol || !params->hmc_colsum || params->n_leapfrog < 0))
     return fail(FLOWMC_ERR_INVALID, "local_steps: HMC needs hmc_chol, hmc_colsum and n_leapfrog >= 0");
 
   // take_steps.py:71: rng_key, subkey = split(rng_key)

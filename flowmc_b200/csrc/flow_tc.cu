@@ -169,6 +169,9 @@ struct TcArgs {
   uint8_t* act_img;   // per (tile, layer): conditioner input and hidden activations as packed B stages (K = the
                       // tile's 128 rows) for the tensor-core weight-gradient GEMMs (flow_tc.cuh: tc_act_*)
   long long* timing;  // optional diagnostics: [3][256] clock64 stamps of CTA 0 (producer, MMA issuer, epilogue thread 0)
+  int dump_vec;       // training forward: activation images leave with st.global.v4 (1) or bulk stores (0)
+  int dbg_skip;       // TIMING EXPERIMENTS ONLY (FLOWMC_TC_DBG_SKIP): 1 = no activation-image dump, 2 = no theta dump,
+                      // 4 = no layer-input save -- the results are then useless to the backward pass
 };
 
 #define TC_STAMP(role)                                                     \
@@ -181,15 +184,28 @@ struct TcSmem {
   uint64_t a_ready[4];  // per K-chunk (32 columns) of the A operand: a GEMM starts on the first chunk while the
                         // epilogue threads are still writing the later ones
   uint64_t peer_full[2 * TC_STAGES];  // CTA pair, leader only: the peer CTA's half of a weight stage has landed
+  uint64_t xbar[2];  // feature split: [0] "my tile may be written" (every epilogue warp of every CTA of the cluster
+                     // arrives once per layer), [1] "all transformed features / log-det partials have been exchanged"
   uint32_t tmem_base;
   float ldpart[TC_PARTS][TC_M];
+  alignas(16) float ldx[8][TC_M];  // feature split: per-CTA log-det partial sums of the tile (summed on rank 0)
 };
 
 
-template <int KB, int MODE, bool PAIR>
+// SPLIT (training forward only): a cluster of R = 2, 4 or 8 CTAs shares ONE tile.  Every CTA keeps the whole tile in
+// its shared memory and runs the two tanh layers redundantly, but takes only every R-th chunk of spline features
+// (chunk index % R == cluster rank): the W3 GEMMs and the spline epilogues -- 3/4 of a layer's MMAs, nearly all of its
+// MUFU work -- divide by R.  After a layer each CTA has written its transformed features into every peer's tile
+// through distributed shared memory (st.shared::cluster) and one mbarrier round synchronises the cluster; log-det
+// partial sums are reduced on rank 0 in rank order (deterministic).  This is what lets a data-parallel rank that
+// holds only a few tiles (batch / n_gpus rows) use all of its SMs: per-tile latency, not throughput, bounds a
+// training step.
+template <int KB, int MODE, bool PAIR, bool SPLIT = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlowDesc D, const TcProgram PR,
                                                                 const TcArgs a) {
   constexpr int NP = 3 * KB + 1;
+  static_assert(!(PAIR && SPLIT), "CTA pairs and the feature split are alternative cluster modes");
+  static_assert(!SPLIT || MODE == TC_TRAIN, "the feature split is built for the training forward pass");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stages = smem;                                             // the weight ring, 1024-aligned slots
@@ -208,6 +224,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
   // transformed features, feature-ordinal major]
   float* sbias_all = xs + TC_M * xs_stride;
   const int bias_stride = (D.n_linear - 1) * 128 + ((d + 1) / 2) * NP;
+  // feature split: exchange buffer [transformed-feature ordinal][row] (16-byte aligned), after the biases
+  float* xstage = sbias_all + ((D.n_layers * bias_stride + 3) & ~3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* astage_all = stages + (size_t)(TC_STAGES - 1) * TC_STAGE_BYTES;  // training only, see NST
   const float* P = a.params;
@@ -217,6 +235,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
   // biases carry over from tile to tile; the weight stream of the next tile runs under the tail of this one)
   const int64_t n_tiles_real = (a.n + TC_M - 1) / TC_M;
   const int64_t n_tiles = PAIR ? ((n_tiles_real + 1) & ~(int64_t)1) : n_tiles_real;
+  // feature split: cluster c takes tiles c, c + n_clusters, ...; rank r of the cluster takes the chunks with index % R == r
+  const uint32_t R = SPLIT ? tc::cluster_size() : 1u;
+  const int64_t tile_first = SPLIT ? (int64_t)(blockIdx.x / R) : (int64_t)blockIdx.x;
+  const int64_t tile_step = SPLIT ? (int64_t)(gridDim.x / R) : (int64_t)gridDim.x;
   // PAIR: two CTAs on neighbouring SMs (a 2-CTA cluster) run their two tiles through the same schedule as ONE
   // M = 256 problem (tcgen05.mma.cta_group::2): each CTA keeps its own rows of A and D in its tensor memory and
   // streams only HALF of every weight stage (N / 2 rows of the hi and lo images) into its shared memory -- the
@@ -224,7 +246,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
   // (cluster rank 0) issues every MMA; the peer's MMA warp only relays "my half of stage s has landed"; epilogue
   // threads of both CTAs signal the leader's operand / accumulator barriers; MMA completions are committed to the
   // barriers of both CTAs.
-  const uint32_t crank = PAIR ? tc::cluster_rank() : 0u;
+  const uint32_t crank = (PAIR || SPLIT) ? tc::cluster_rank() : 0u;
+  auto skip_item = [&](const TcItem& it, int ii) -> bool {  // a spline chunk that another CTA of the cluster owns
+    return SPLIT && it.kind == 1 && (uint32_t)(ii - (D.n_linear - 1)) % R != crank;
+  };
   constexpr uint32_t kEpiArrivals = (PAIR ? 2 : 1) * TC_EPI_WARPS;  // one arrival per epilogue warp
   if (warp == TC_EPI_WARPS + 1 && lane == 0) {
     for (int i = 0; i < NST; ++i) {
@@ -237,6 +262,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
       tc::mbar_init(&S->acc_empty[i], kEpiArrivals);
     }
     for (int i = 0; i < 4; ++i) tc::mbar_init(&S->a_ready[i], kEpiArrivals);
+    tc::mbar_init(&S->xbar[0], (SPLIT ? R : 1u) * TC_EPI_WARPS);  // control: one arrival per epilogue warp of the cluster
+    tc::mbar_init(&S->xbar[1], 1);  // data: one local arrive.expect_tx per round + the peers' st.async bytes
     tc::fence_mbar_init();
   }
   if (warp == TC_EPI_WARPS) {
@@ -245,7 +272,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (PAIR) tc::cluster_sync();  // both CTAs' barriers and tensor memory exist before anything crosses over
+  if (PAIR || SPLIT) tc::cluster_sync();  // every CTA's barriers and tensor memory exist before anything crosses over
   tc::tc_fence_after();
   // epilogue -> MMA warp signal, called by whole warps (every lane has fenced its tensor-memory accesses): one
   // arrival per warp -- in a pair the barrier lives in the leader CTA, and 256 remote arrivals per hand-off cost
@@ -265,7 +292,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     {
       uint32_t s = 0, ph = 0;
       int n_stamp = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int64_t tile = tile_first; tile < n_tiles; tile += tile_step)
       for (int pass = 0; pass < n_pass; ++pass) {
         const bool inv = (MODE == TC_INV) || (MODE == TC_NF && pass == 0);
         for (int li = 0; li < L; ++li) {
@@ -273,6 +300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
           const uint8_t* lbase = a.image + tc_layer_base(D, PR, l);
           for (int ii = 0; ii < PR.n_items[p]; ++ii) {
             const TcItem& it = PR.items[p][ii];
+            if (skip_item(it, ii)) continue;
             const uint32_t bytes = 2u * it.npad * 128u;
             for (int kc = 0; kc < it.n_kc; ++kc) {
               tc::mbar_wait(&S->stage_empty[s], ph ^ 1);
@@ -303,7 +331,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     if (PAIR && crank != 0) {
       // peer CTA of a pair: no MMAs to issue; relay the arrival of this CTA's half of every weight stage
       uint32_t s = 0, ph = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int64_t tile = tile_first; tile < n_tiles; tile += tile_step)
       for (int pass = 0; pass < n_pass; ++pass)
         for (int li = 0; li < L; ++li) {
           const int p = (((MODE == TC_INV) || (MODE == TC_NF && pass == 0)) ? L - 1 - li : li) & 1;
@@ -318,14 +346,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     } else {
       uint32_t s = 0, ph = 0, seq = 0, a_ph = 0;
       int n_stamp = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int64_t tile = tile_first; tile < n_tiles; tile += tile_step)
       for (int pass = 0; pass < n_pass; ++pass) {
         const bool inv = (MODE == TC_INV) || (MODE == TC_NF && pass == 0);
         for (int li = 0; li < L; ++li) {
           const int l = inv ? L - 1 - li : li, p = l & 1;
+          bool first_chunk = true;  // the first spline chunk THIS CTA runs in the layer picks up the h_last operand
           for (int ii = 0; ii < PR.n_items[p]; ++ii) {
             const TcItem it = PR.items[p][ii];
-            const bool new_a = it.kind == 0 || it.lin == 0;  // a new A operand: masked x, h1, ..., h_last
+            if (skip_item(it, ii)) continue;
+            const bool new_a = it.kind == 0 || first_chunk;  // a new A operand: masked x, h1, ..., h_last
+            if (it.kind == 1) first_chunk = false;
             const uint32_t slot = seq & 1;
             tc::mbar_wait(&S->acc_empty[slot], ((seq >> 1) & 1) ^ 1);
             tc::tc_fence_after();
@@ -400,9 +431,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     // one lane sends the hi and the lo block with two bulk stores (asynchronous, full lines, off the LSU store
     // path, which the scattered 4-byte stores of a direct dump saturate).
     uint8_t* astage = astage_all + warp * 4096;
+    // a.dump_vec (FLOWMC_TC_DUMP=vec, the default): the staged block leaves with coalesced 16-byte st.global from
+    // all 32 lanes instead -- the bulk stores queue behind the weight stream in the SM's TMA unit, and waiting for
+    // the previous one to release the buffer (bulk_wait_read) was what tripled the tanh epilogues of the training
+    // forward (10.5K against 3.4K cycles, profiles/r02 timelines).
     auto dump_rows = [&](auto nb_tag, const uint32_t* hi, const uint32_t* lo, int n0, uint8_t* gimg, int n_rows) {
       constexpr int NB = decltype(nb_tag)::value;
-      if (lane == 0) tc::bulk_wait_read<0>();  // the previous rows have left the buffer
+      if (a.dbg_skip & 1) return;
+      if (!a.dump_vec && lane == 0) tc::bulk_wait_read<0>();  // the previous rows have left the buffer
       __syncwarp();
       uint32_t* st = reinterpret_cast<uint32_t*>(astage);
 #pragma unroll
@@ -410,6 +446,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
         const int o = tc::packed_b_offset(u, lane) >> 2;
         st[o] = hi[u];
         st[NB * 32 + o] = lo[u];
+      }
+      if (a.dump_vec) {
+        __syncwarp();
+        const float4* s4 = reinterpret_cast<const float4*>(astage);
+        float4* ghi = reinterpret_cast<float4*>(gimg + (size_t)n0 * 128);
+        float4* glo = reinterpret_cast<float4*>(gimg + (size_t)(n_rows + n0) * 128);
+#pragma unroll
+        for (int v = 0; v < NB / 4; ++v) {  // NB * 128 bytes per block = NB * 8 float4 = NB / 4 per lane
+          __stcs(ghi + v * 32 + lane, s4[v * 32 + lane]);
+          __stcs(glo + v * 32 + lane, s4[NB * 8 + v * 32 + lane]);
+        }
+        return;
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
@@ -424,6 +472,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     int g_lo, g_hi;
     part(g_all, g_lo, g_hi);
     const int j_lo = g_lo * 8, j_hi = min(d, g_hi * 8);
+    // feature split: remote addresses of this thread's tile row in the peer CTAs, phases of the two cluster barriers
+    uint32_t x_ph0 = 0, x_ph1 = 0;
+    // which transformed-feature ordinals (feature f = parity + 2 * ordinal) this CTA owns: bit o of the mask
+    // (one mask serves both layer parities: chunk c = ordinals [c * fc, (c + 1) * fc) belongs to rank c % R)
+    uint64_t own_mask = ~0ull;
+    if (SPLIT) {
+      const int fc_split = PR.items[0][D.n_linear - 1].n_feat;  // features per (full) spline chunk
+      own_mask = 0;
+      for (int o = 0; o < (d + 1) / 2; ++o)
+        if ((uint32_t)(o / fc_split) % R == crank) own_mask |= 1ull << o;
+    }
+    // does this CTA transform feature j in layer l?  (j is one of the layer's transformed features)
+    auto owns_feature = [&](int j, int l) -> bool { return !SPLIT || ((own_mask >> ((j - (l & 1)) >> 1)) & 1ull) != 0; };
+    // Data exchange round: the peers' values arrive as bulk copies (shared memory -> peer shared memory) that complete
+    // bytes on THIS CTA's xbar[1]; one thread announces how many bytes the round brings (arrive.expect_tx), everyone
+    // waits for the phase.  No release fences: the sender's global stores (activation dumps) are not drained, and
+    // no per-element remote stores (4-byte st.async packets cost ~16K cycles per layer, profiles/r02 notes).
+    // send n_bytes at float offset `off` of xstage / of S->ldx to the same place in every peer (tid 0 only)
+    auto send_block = [&](const float* src, uint32_t n_bytes, bool to_rank0_only) {
+      for (uint32_t rk = 0; rk < (to_rank0_only ? 1u : R); ++rk)
+        if (rk != crank) tc::bulk_s2peer(tc::mapa_u32(src, rk), src, n_bytes, tc::mapa_u32(&S->xbar[1], rk));
+    };
+    auto expect_round = [&](uint32_t bytes) {
+      if (tid == 0) tc::mbar_arrive_expect_tx(&S->xbar[1], bytes);
+    };
+    auto wait_round = [&]() {
+      tc::mbar_wait(&S->xbar[1], x_ph1);
+      x_ph1 ^= 1;
+    };
 
     // stage every layer's biases (once per CTA; visible after the epi_bar that follows).  Flattened over (layer, entry) with 8
     // independent loads in flight per thread: the naive per-layer loop cost ~16K cycles of serialised L2 latency.
@@ -457,7 +534,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     epi_bar();
     uint32_t seq = 0;
     int n_stamp = (tid == 0) ? 0 : 256;
-    for (tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (tile = tile_first; tile < n_tiles; tile += tile_step) {
     row0 = tile * TC_M;
     grow = row0 + row;
     r = min(grow, a.n - 1);
@@ -497,9 +574,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     // the tile (all rows, complete after an epi_bar) -> save_x[slot]: rows are contiguous in global memory, so the
     // CTA writes them as one coalesced stream
     auto save_tile = [&](int slot) {
+      if (a.dbg_skip & 4) return;
       const int64_t rows = min((int64_t)TC_M, a.n - row0);
       float* dst = a.save_x + ((int64_t)slot * a.n + row0) * d;
-      for (int e = tid; e < (int)rows * d; e += TC_EPI) {
+      // feature split: every CTA holds the whole tile; rank r writes its share of the rows
+      const int e_lo = SPLIT ? (int)(crank * (TC_M / R)) * d : 0;
+      const int e_hi = SPLIT ? min((int)rows, (int)((crank + 1) * (TC_M / R))) * d : (int)rows * d;
+      for (int e = e_lo + tid; e < e_hi; e += TC_EPI) {
         const int rr = e / d;
         dst[e] = xs[rr * xs_stride + (e - rr * d)];
       }
@@ -518,6 +599,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
         if (MODE == TC_TRAIN && a.save_x != nullptr) {
           save_tile(l);
           epi_bar();  // the affine below rewrites the tile
+          if (SPLIT) TC_STAMP(2);  // (split) layer input saved
         }
         // ---- ScalarAffine (rqSpline.py:435-436) + A operand = x * mask, hi / lo ------------------
         {
@@ -529,30 +611,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
               const int j = g * 8 + u;
               float v = 0.0f;
               if (j < d) {
-                v = xr[j];
-                v = inv ? v * e - shift : (v + shift) * e;
-                xr[j] = v;
-                if (((j + l) & 1) == 0) v = 0.0f;  // transformed features do not feed the conditioner
+                const bool transformed = ((j + l) & 1) == 0;
+                // feature split: a transformed feature another CTA owns stays untouched here -- the owner's result
+                // will overwrite it (its old value is needed by nobody in this CTA)
+                if (!(SPLIT && transformed && !owns_feature(j, l))) {
+                  v = xr[j];
+                  v = inv ? v * e - shift : (v + shift) * e;
+                  xr[j] = v;
+                }
+                if (transformed) v = 0.0f;  // transformed features do not feed the conditioner
               }
               tc::split_tf32(v, hi[u], lo[u]);
             }
             tc::tmem_st8(t_ahi + lane_base + g * 8, hi);
             tc::tmem_st8(t_alo + lane_base + g * 8, lo);
-            if (MODE == TC_TRAIN && a.act_img != nullptr && row0 < a.n) {
+            if (MODE == TC_TRAIN && a.act_img != nullptr && row0 < a.n && (!SPLIT || (uint32_t)g % R == crank)) {
               const int npx = tc_pad16(d);
               dump_rows(std::integral_constant<int, 8>{}, hi, lo, g * 8,
                         a.act_img + (tile * L + l) * tc_act_layer_bytes(D) + (size_t)q * 2 * npx * 128, npx);
             }
           }
-          if (hf == 0) ldacc += inv ? -(float)d * scale : (float)d * scale;
+          if (hf == 0 && crank == 0) ldacc += inv ? -(float)d * scale : (float)d * scale;
+          if (SPLIT) TC_STAMP(2);  // (split) affine loop done
           tc::tmem_wait_st();
           tc::tc_fence_before();
           for (int kc = 0; kc < PR.items[p][0].n_kc; ++kc) arrive_mma(&S->a_ready[kc]);
+          if (SPLIT) {
+            // announce this layer's exchange round BEFORE any peer can be released into sending: the layer brings
+            // (transformed features of the layer - those this CTA owns) x 128 rows x 4 bytes
+            int owned = 0;
+            for (int ii = nh; ii < PR.n_items[p]; ++ii)
+              if (!skip_item(PR.items[p][ii], ii)) owned += PR.items[p][ii].n_feat;
+            expect_round((uint32_t)(((d - p + 1) / 2 - owned) * TC_M * 4));
+          }
           epi_bar();  // the row's other thread reads these x values in the spline stage
           TC_STAMP(2);  // affine + operand written
+          if (SPLIT && lane == 0) {
+            // this warp no longer reads the layer's input (save_tile and the affine are done; the bar.sync above
+            // ordered every thread's shared-memory accesses): the peers may write their transformed features into
+            // this CTA's tile
+            for (uint32_t rk = 0; rk < R; ++rk) tc::mbar_arrive_remote_relaxed(&S->xbar[0], rk);
+          }
         }
+        bool peers_ready = !SPLIT;
         for (int ii = 0; ii < PR.n_items[p]; ++ii) {
           const TcItem& it = PR.items[p][ii];
+          if (skip_item(it, ii)) continue;
           const uint32_t slot = seq & 1;
           const uint32_t t_acc = tbase + 256 + slot * 128 + lane_base;
           tc::mbar_wait(&S->acc_full[slot], (seq >> 1) & 1);
@@ -580,7 +684,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
                   if (MODE == TC_TRAIN && a.save_h != nullptr && grow < a.n)
                     a.save_h[((int64_t)(l * nh + it.lin) * 128 + c + u) * a.n + grow] = hv;
                 }
-                if (MODE == TC_TRAIN && a.act_img != nullptr && row0 < a.n) {
+                if (MODE == TC_TRAIN && a.act_img != nullptr && row0 < a.n &&
+                    (!SPLIT || (uint32_t)(c >> 4) % R == crank)) {  // split: the redundant copies share the dump
                   uint8_t* gimg = a.act_img + (tile * L + l) * tc_act_layer_bytes(D) +
                                   tc_act_item_off(D, it.lin + 1) + (size_t)q * 2 * N * 128;
                   dump_rows(std::integral_constant<int, 16>{}, hi, lo, c, gimg, N);
@@ -615,7 +720,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
               }
 #pragma unroll
               for (int u = 0; u < NP && u < 32; ++u) raw[u] = v[u] + bl[i * NP + u];
-              if (MODE == TC_TRAIN && a.save_theta != nullptr && grow < a.n) {
+              if (MODE == TC_TRAIN && a.save_theta != nullptr && grow < a.n && !(a.dbg_skip & 2)) {
                 float* dst = a.save_theta + ((int64_t)l * ((d + 1) / 2) + it.lin + i) * NP * a.n + grow;
 #pragma unroll
                 for (int u = 0; u < NP; ++u) dst[(int64_t)u * a.n] = raw[u];
@@ -635,22 +740,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
               xr[f1] = y1;
               ldacc += t0;
               ldacc += t1;
+              if (SPLIT) {
+                xstage[(it.lin + i) * TC_M + row] = y0;
+                xstage[(it.lin + i + 1) * TC_M + row] = y1;
+              }
             }
             if (i < i_hi) {
               float raw0[NP], t0;
               load_raw(i, raw0);
               const int f0 = p + 2 * (it.lin + i);
-              xr[f0] = inv ? rq_apply_fast<KB, true>(raw0, D.range_min, D.range_max, xr[f0], t0)
-                           : rq_apply_fast<KB, false>(raw0, D.range_min, D.range_max, xr[f0], t0);
+              const float y0 = inv ? rq_apply_fast<KB, true>(raw0, D.range_min, D.range_max, xr[f0], t0)
+                                   : rq_apply_fast<KB, false>(raw0, D.range_min, D.range_max, xr[f0], t0);
+              xr[f0] = y0;
               ldacc += t0;
+              if (SPLIT) xstage[(it.lin + i) * TC_M + row] = y0;
             }
             tc::tc_fence_before();
             arrive_mma(&S->acc_empty[slot]);
+            if (SPLIT) {
+              // the chunk's features [it.lin, it.lin + n_feat) x 128 rows are one contiguous block of the exchange
+              // buffer: one bulk copy per peer, once every CTA of the cluster has finished reading the layer's input
+              tc::fence_proxy_async_smem();  // every thread's exchange-buffer writes -> visible to the bulk copy engine
+              epi_bar();
+              if (tid == 0) {
+                if (!peers_ready) tc::mbar_wait(&S->xbar[0], x_ph0);
+                send_block(xstage + it.lin * TC_M, (uint32_t)(nf * TC_M * 4), false);
+              }
+              if (!peers_ready) {
+                if (tid != 0) tc::mbar_wait(&S->xbar[0], x_ph0);
+                peers_ready = true;
+              }
+            }
           }
           TC_STAMP(2);  // item epilogue done
           ++seq;
         }
-        epi_bar();  // both threads of a row see each other's feature updates
+        if (SPLIT) {
+          // threads that wrote nothing still consume this layer's phase of xbar[0]; then the exchange round: every
+          // CTA's transformed features have landed in every tile copy (also orders the row's two threads, like epi_bar)
+          if (!peers_ready) tc::mbar_wait(&S->xbar[0], x_ph0);
+          x_ph0 ^= 1;
+          TC_STAMP(2);   // (split) guard consumed
+          wait_round();  // every peer's chunks have landed in the exchange buffer
+          TC_STAMP(2);   // (split) exchange round complete
+          {              // ... copy the features other CTAs transformed into this CTA's tile (the row's two threads
+                         // take alternate ordinals)
+            const int ntf = (d - p + 1) / 2;
+            for (int o = hf; o < ntf; o += TC_PARTS)
+              if (((own_mask >> o) & 1ull) == 0) xr[p + 2 * o] = xstage[o * TC_M + row];
+          }
+          epi_bar();  // both threads of a row see each other's (and the peers') feature updates
+        } else {
+          epi_bar();  // both threads of a row see each other's feature updates
+        }
       }
       if (MODE == TC_NF && pass == 0) {
         // proposal = inverse * sqrt(diag data_cov) + data_mean (rqSpline.py:495); keep it; re-whiten (rqSpline.py:501)
@@ -671,7 +813,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     S->ldpart[hf][row] = ldacc;
     epi_bar();
     const int post = (MODE == TC_NF) ? POST_BASE_LOGP : a.post;
-    if (post == POST_BASE_LOGP) {
+    if (SPLIT) {
+      // log-det of the row = sum over the cluster's CTAs of their chunks' contributions: every CTA sends its sum to
+      // rank 0, which adds them in rank order
+      expect_round(crank == 0 ? (R - 1u) * TC_M * 4u : 0u);
+      if (hf == 0) {
+        float ldsum = S->ldpart[0][row];
+#pragma unroll
+        for (int w = 1; w < TC_PARTS; ++w) ldsum += S->ldpart[w][row];
+        S->ldx[crank][row] = ldsum;
+      }
+      tc::fence_proxy_async_smem();
+      epi_bar();
+      if (tid == 0 && crank != 0) send_block(&S->ldx[crank][0], TC_M * 4u, true);
+      wait_round();
+      if (crank == 0 && hf == 0 && grow < a.n) {
+        float ldsum = S->ldx[0][row];
+        for (uint32_t k = 1; k < R; ++k) ldsum += S->ldx[k][row];
+        if (post == POST_BASE_LOGP) a.ldout[grow] = ldsum + base_log_prob(D, P, xr);
+        else if (a.ldout != nullptr) a.ldout[grow] = ldsum;
+      }
+    } else if (post == POST_BASE_LOGP) {
       if (hf == 0 && grow < a.n) {
         float ldsum = S->ldpart[0][row];
 #pragma unroll
@@ -699,7 +861,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     tc::tc_fence_before();
   }
   __syncthreads();
-  if (PAIR) tc::cluster_sync();  // neither CTA leaves while the other may still touch its barriers / tensor memory
+  if (PAIR || SPLIT) tc::cluster_sync();  // no CTA leaves while another may still touch its barriers / shared / tensor memory
   tc::tc_fence_after();
   if (warp == TC_EPI_WARPS) {
     if (PAIR) tc::tmem_dealloc_pair<512>(tbase);
@@ -761,6 +923,100 @@ static int launch_tc_impl(const FlowmcFlowDesc& D, const TcProgram& PR, const Tc
   return FLOWMC_OK;
 }
 
+// dynamic shared memory of the split training-forward kernel: the one-CTA layout + the exchange buffer
+static size_t tc_split_smem_bytes(const FlowmcFlowDesc& D) {
+  return 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + ((sizeof(TcSmem) + 15) & ~15) +
+         (size_t)TC_M * (D.n_features + 1) * sizeof(float) +
+         (size_t)D.n_layers * ((D.n_linear - 1) * 128 + ((D.n_features + 1) / 2) * (3 * D.num_bins + 1)) * sizeof(float) +
+         16 + (size_t)((D.n_features + 1) / 2) * TC_M * sizeof(float);
+}
+
+// co-resident clusters of R CTAs of the split training-forward kernel on this device (0 = unknown yet)
+static int g_split_max_clusters[9] = {0};
+
+// Feature split of the training forward pass: clusters of R CTAs per tile (see the kernel).  Returns the cluster size
+// to use (1 = not applicable: the caller runs the one-CTA-per-tile kernel).
+int tc_split_factor(const FlowmcFlowDesc& D, int64_t tiles) {
+  TcProgram PR;
+  if (tc_build_program(D, &PR)) return 1;
+  static const int forced = [] {
+    const char* e = std::getenv("FLOWMC_TC_SPLIT");  // 0 = off, 2 / 4 / 8 = force this cluster size, unset = automatic
+    return e != nullptr ? std::atoi(e) : -1;
+  }();
+  if (forced == 0 || tc_split_smem_bytes(D) > 227 * 1024) return 1;
+  const int nh = D.n_linear - 1;
+  const int chunks = (PR.n_items[0] < PR.n_items[1] ? PR.n_items[0] : PR.n_items[1]) - nh;  // per layer, both parities
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+  }
+  int r = 1;
+  if (forced > 1) {
+    r = forced;
+  } else {
+    // automatic: the largest cluster that still gives every tile its own cluster in ONE wave.  Clusters are placed
+    // inside a GPC, so fewer 8-CTA clusters fit than SMs / 8 (measured through cudaOccupancyMaxActiveClusters by the
+    // first launch of each size; until then a conservative guess).
+    auto fits = [&](int rr) {
+      const int cap = g_split_max_clusters[rr] > 0 ? g_split_max_clusters[rr] : (rr == 8 ? 12 : n_sm / rr - (rr == 4 ? 4 : 0));
+      return tiles <= cap;
+    };
+    while (r < 8 && fits(2 * r)) r *= 2;
+  }
+  while (r > 1 && r > chunks) r /= 2;  // every CTA needs at least one chunk per layer (barrier phases stay aligned)
+  return (r == 2 || r == 4 || r == 8) ? r : 1;
+}
+
+template <int KB>
+static int launch_tc_split(const FlowmcFlowDesc& D, const TcProgram& PR, const TcArgs& a, int R, cudaStream_t stream) {
+  auto kern = flow_tc_kernel<KB, TC_TRAIN, false, true>;
+  const size_t bytes = tc_split_smem_bytes(D);
+  static size_t configured = 0;
+  if (bytes > configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      flowmc_set_error("flow (tensor-core path, feature split): cannot configure the kernel");
+      return FLOWMC_ERR_CUDA;
+    }
+    configured = bytes;
+  }
+  const unsigned tiles = (unsigned)((a.n + TC_M - 1) / TC_M);
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)R;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // co-resident clusters of this size on this device (cached per cluster size)
+  int* max_clusters = g_split_max_clusters;
+  if (max_clusters[R] == 0) {
+    cfg.gridDim = dim3((unsigned)R);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = 148 / (R == 8 ? 9 : R);  // conservative
+    }
+    max_clusters[R] = n;
+  }
+  const unsigned n_clusters = tiles < (unsigned)max_clusters[R] ? tiles : (unsigned)max_clusters[R];
+  cfg.gridDim = dim3(n_clusters * (unsigned)R);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, D, PR, a);
+  flowmc_count_launch();
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    flowmc_set_error(cudaGetErrorString(e));
+    return FLOWMC_ERR_CUDA;
+  }
+  return FLOWMC_OK;
+}
+
 // FLOWMC_TC_PAIR=1 runs the tiles as CTA pairs (cta_group::2, M = 256: each SM streams half of the weights, 8-slot
 // ring).  Verified against the oracle like the default path, but measured SLOWER on B200 (C4 log_prob 86 M vs
 // 100 M samples/s): the flow's GEMMs are short and separated by dependent epilogues, so every one of the ~15
@@ -804,9 +1060,28 @@ int flow_transform_tc(const FlowmcFlowDesc& D, bool inverse, const float* P, con
   a.rows_per_key = rpk;
   a.save_x = save_x; a.save_h = save_h; a.save_theta = save_theta; a.act_img = act_img;
   a.timing = g_tc_timing;
+  static const int dump_vec = [] {
+    const char* e = std::getenv("FLOWMC_TC_DUMP");
+    return (e != nullptr && e[0] == 'b') ? 0 : 1;  // "bulk" selects the cp.async.bulk stores
+  }();
+  a.dump_vec = dump_vec;
+  static const int dbg_skip = [] {
+    const char* e = std::getenv("FLOWMC_TC_DBG_SKIP");
+    return e != nullptr ? std::atoi(e) : 0;
+  }();
+  a.dbg_skip = dbg_skip;
   if (inverse) return dispatch_tc<TC_INV>(D, PR, a, stream);
-  if (save_x != nullptr || save_h != nullptr || save_theta != nullptr || act_img != nullptr)
+  if (save_x != nullptr || save_h != nullptr || save_theta != nullptr || act_img != nullptr) {
+    // few tiles (a data-parallel rank's slice of the batch): clusters of CTAs share a tile, see flow_tc_kernel
+    const int R = (save_h == nullptr && D.num_bins <= 8) ? tc_split_factor(D, (n + TC_M - 1) / TC_M) : 1;
+    if (R > 1) {
+      switch (D.num_bins) {
+        case 4: return launch_tc_split<4>(D, PR, a, R, stream);
+        case 8: return launch_tc_split<8>(D, PR, a, R, stream);
+      }
+    }
     return dispatch_tc<TC_TRAIN>(D, PR, a, stream);
+  }
   return dispatch_tc<TC_FWD>(D, PR, a, stream);
 }
 

@@ -22,6 +22,7 @@
 // gradient MMAs of unit u, dW store of unit u-1 under the data-gradient MMAs of unit u); the weight producer
 // prefetches the next items' stages through a 3-deep ring meanwhile.
 // TMEM map: [0,128) A hi | [128,256) A lo | [256,384) acc 0 (data gradient) | [384,512) acc 1 (weight gradient).
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -165,18 +166,28 @@ __device__ __forceinline__ void bt_reduce_layer(const FlowmcFlowDesc& D, const f
                                                 int g_end);
 __device__ __forceinline__ float bt_reduce_loss(const float* partial, int64_t pstride, int n_cta);
 
+// PARTS = epilogue threads per sample row: 2 (default) or 4 (16 epilogue warps, 576 threads, 96 registers per thread:
+// an experiment that measured slower, see flow_backward_tc).
+template <int PARTS>
 struct BtSmem {
   uint64_t stage_full[BT_STAGES], stage_empty[BT_STAGES], acc_full;
   uint64_t a_ready[4];  // per K-chunk (32 columns) of the A operand, one arrival per epilogue warp
   uint32_t tmem_base;
-  float red[2 * TC_EPI_WARPS];
-  float bsum[TC_PARTS][TC_M];
+  float red[2 * 4 * PARTS];
+  float bsum[PARTS][TC_M];
 };
 
-template <int KB>
-__global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const FlowmcFlowDesc D, const BtProgram PR,
-                                                                         const BtArgs a) {
+template <int N>
+__device__ __forceinline__ void bt_bar() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
+
+template <int KB, int PARTS>
+__global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kernel(const FlowmcFlowDesc D,
+                                                                                 const BtProgram PR, const BtArgs a) {
   constexpr int NP = 3 * KB + 1;
+  constexpr int EPI_WARPS = 4 * PARTS, EPI = EPI_WARPS * 32;
+  constexpr int CPT = 128 / PARTS;  // accumulator / operand columns per epilogue thread of a row
+  auto epi_bar = [] { bt_bar<EPI>(); };
+  using BtSmem = flowmc::BtSmem<PARTS>;
   if ((int)blockIdx.x < a.n_cta) {  // ===== tile CTA (CTAs beyond n_cta only reduce, below) =====
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -191,23 +202,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
   const int L = D.n_layers, nh = D.n_linear - 1;
   const int64_t n = a.n;
 
-  if (warp == TC_EPI_WARPS + 1 && lane == 0) {
+  if (warp == EPI_WARPS + 1 && lane == 0) {
     for (int i = 0; i < BT_STAGES; ++i) {
       tc::mbar_init(&S->stage_full[i], 1);
       tc::mbar_init(&S->stage_empty[i], 1);
     }
     tc::mbar_init(&S->acc_full, 1);
-    for (int i = 0; i < 4; ++i) tc::mbar_init(&S->a_ready[i], TC_EPI_WARPS);
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&S->a_ready[i], EPI_WARPS);
     tc::fence_mbar_init();
   }
-  if (warp == TC_EPI_WARPS) tc::tmem_alloc<512>(&S->tmem_base);
+  if (warp == EPI_WARPS) tc::tmem_alloc<512>(&S->tmem_base);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tbase = S->tmem_base;
   const uint32_t t_ahi = tbase, t_alo = tbase + 128;
 
-  if (warp == TC_EPI_WARPS) {
+  if (warp == EPI_WARPS) {
     // ===== B-stage producer ====================================================================
     uint32_t s = 0, ph = 0;
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += a.n_cta)
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
         }
       }
     }
-  } else if (warp == TC_EPI_WARPS + 1) {
+  } else if (warp == EPI_WARPS + 1) {
     // ===== MMA issuer ==========================================================================
     uint32_t s = 0, ph = 0, a_ph = 0;
     for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += a.n_cta)
@@ -279,7 +290,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
     uint32_t f_ph = 0;
     int n_stamp = 0;
     auto part = [&](int cnt, int& lo, int& hi) {
-      const int per = (cnt + TC_PARTS - 1) / TC_PARTS;
+      const int per = (cnt + PARTS - 1) / PARTS;
       lo = min(cnt, hf * per);
       hi = min(cnt, lo + per);
     };
@@ -363,11 +374,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
       if (it.kind == BK_DG3) {
         const float shift = PL[D.off_shift], e = expf(PL[D.off_scale]);
         const float* xin = a.save_x + ((int64_t)l * n + r) * d;
-        // chunks owned by the row's other thread: nothing to add
-        for (int kc = 1 - hf; kc < it.n_feat; kc += 2) arrive_chunk(kc);
+        // chunks owned by the row's other threads: nothing to add
+        for (int kc = 0; kc < it.n_feat; ++kc)
+          if (kc % PARTS != hf) arrive_chunk(kc);
 #pragma unroll
-        for (int sg = 0; sg < 2; ++sg) {
-          const int fi = 2 * sg + hf;
+        for (int sg = 0; sg < 4 / PARTS; ++sg) {
+          const int fi = PARTS * sg + hf;
           if (fi < it.n_feat) {
             const int fo = it.lin + fi, f = p + 2 * fo;
             float raw[NP], dr[32], gx;
@@ -494,8 +506,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
       const bool permuted = (ncols & 3) == 0;
       const int npad = tc_pad16(ncols);
 #pragma unroll 1
-      for (int g2 = 0; g2 < 2; ++g2) {
-        const int c0 = hf * 64 + g2 * 32;
+      for (int g2 = 0; g2 < CPT / 32; ++g2) {
+        const int c0 = hf * CPT + g2 * 32;
         if (c0 < npad) {
           float v[32];
           tc::tmem_ld16(tbase + 384 + lane_base + c0, v);
@@ -517,7 +529,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
         }
       }
       // bias gradient = row sum of dY^T (both halves of the tile's samples)
-      if (hf == 0 && active) acc_to(GL + boff, S->bsum[0][t] + S->bsum[1][t]);
+      if (hf == 0 && active) {
+        float bs = S->bsum[0][t];
+#pragma unroll
+        for (int h2 = 1; h2 < PARTS; ++h2) bs += S->bsum[h2][t];
+        acc_to(GL + boff, bs);
+      }
     };
     // masked coupling + ScalarAffine adjoints of layer l (acc 0 holds the conditioner-input gradient)
     auto finish_layer = [&](int l) {
@@ -552,14 +569,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
       }
       if (lane == 0) {
         S->red[warp] = ssc;
-        S->red[TC_EPI_WARPS + warp] = ssh;
+        S->red[EPI_WARPS + warp] = ssh;
       }
       epi_bar();
       if (tid == 0) {
         float sa = 0.0f, sb = 0.0f;
-        for (int w = 0; w < TC_EPI_WARPS; ++w) {
+        for (int w = 0; w < EPI_WARPS; ++w) {
           sa += S->red[w];
-          sb += S->red[TC_EPI_WARPS + w];
+          sb += S->red[EPI_WARPS + w];
         }
         const int n_valid = (int)min((int64_t)TC_M, n - row0);
         acc_to(GL + D.off_scale, sa - a.inv_n * (float)d * (float)n_valid);
@@ -605,10 +622,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
       epi_bar();                                            // T of this unit complete (long since), bsum consumed
       BT_STAMP();
       {                                                     // [E] dY^T: lane = output unit t, columns = the tile's rows
-        const float* src = T + t * BT_TS + hf * 64;
+        const float* src = T + t * BT_TS + hf * CPT;
         float bsum = 0.0f;
 #pragma unroll
-        for (int c = 0; c < 64; c += 8) {
+        for (int c = 0; c < CPT; c += 8) {
           const float4 v0 = *reinterpret_cast<const float4*>(src + c);
           const float4 v1 = *reinterpret_cast<const float4*>(src + c + 4);
           const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -618,8 +635,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
             bsum += v[u];
             tc::split_tf32(v[u], hi[u], lo[u]);
           }
-          tc::tmem_st8(t_ahi + lane_base + hf * 64 + c, hi);
-          tc::tmem_st8(t_alo + lane_base + hf * 64 + c, lo);
+          tc::tmem_st8(t_ahi + lane_base + hf * CPT + c, hi);
+          tc::tmem_st8(t_alo + lane_base + hf * CPT + c, lo);
         }
         S->bsum[hf][t] = bsum;
       }
@@ -641,7 +658,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_backward_tc_kernel(const F
   }
   __syncthreads();
   tc::tc_fence_after();
-  if (warp == TC_EPI_WARPS) tc::tmem_dealloc<512>(tbase);
+  if (warp == EPI_WARPS) tc::tmem_dealloc<512>(tbase);
   }  // tile CTA
   if (a.done == nullptr) return;  // reduction by bt_reduce_kernel
 
@@ -797,10 +814,10 @@ static int bt_sm_count() {
   return sms;
 }
 
-template <int KB>
+template <int KB, int PARTS>
 static int launch_bt(const FlowmcFlowDesc& D, const BtProgram& PR, const BtArgs& a, cudaStream_t stream) {
-  auto kern = flow_backward_tc_kernel<KB>;
-  const size_t bytes = 1024 + (size_t)BT_STAGES * TC_STAGE_BYTES + ((sizeof(BtSmem) + 15) & ~15) +
+  auto kern = flow_backward_tc_kernel<KB, PARTS>;
+  const size_t bytes = 1024 + (size_t)BT_STAGES * TC_STAGE_BYTES + ((sizeof(BtSmem<PARTS>) + 15) & ~15) +
                        (size_t)128 * BT_TS * sizeof(float) + (size_t)TC_M * (D.n_features + 1) * sizeof(float);
   static size_t configured = 0;
   if (bytes > configured) {
@@ -818,7 +835,7 @@ static int launch_bt(const FlowmcFlowDesc& D, const BtProgram& PR, const BtArgs&
   const int n_red = bt_sm_count() - b.n_cta;
   const bool fused = n_red >= 8;
   if (!fused) b.done = nullptr;
-  kern<<<b.n_cta + (fused ? n_red : 0), TC_THREADS, bytes, stream>>>(D, PR, b);
+  kern<<<b.n_cta + (fused ? n_red : 0), 4 * PARTS * 32 + 64, bytes, stream>>>(D, PR, b);
   flowmc_count_launch();
   if (!fused) {
     bt_reduce_kernel<<<dim3(32, D.n_layers), 256, 0, stream>>>(D, b.partial, b.pstride, b.n_cta, b.grad, b.loss);
@@ -876,9 +893,21 @@ int flow_backward_tc(const FlowmcFlowDesc& D, const float* params, uint8_t* wimg
   a.params = params; a.wimg = wimg; a.act_img = act_img; a.save_x = save_x; a.save_theta = save_theta; a.logp = logp;
   a.n = n; a.inv_n = inv_n; a.grad = grad; a.loss = loss; a.timing = g_bt_timing;
   a.partial = partial; a.pstride = pstride; a.n_tiles = tiles; a.done = done; a.n_cta = 0;
-  switch (D.num_bins) {
-    case 4: return launch_bt<4>(D, PR, a, stream);
-    case 8: return launch_bt<8>(D, PR, a, stream);
+  // epilogue threads per sample row: 2.  FLOWMC_BT_PARTS=4 selects 16 epilogue warps -- measured SLOWER on B200
+  // (profiles/r02_prof_train_c4_parts4.txt: C4 backward 562 vs 512 us, C5 783 vs 749 us): with one feature per thread
+  // the adjoint stage shrinks only from 7.4K to 6.2K cycles per unit (it is latency-bound: the spline parameters come
+  // from L2, the MUFU chains are dependent) while the 96-register budget spills and the dW stores contend; the
+  // per-unit chain A-write -> dgrad MMAs -> transposed A-write -> wgrad MMAs through the ONE operand region of tensor
+  // memory is what bounds the kernel, not the epilogue's instruction count.  Kept for A/B runs.
+  static const int parts = [] {
+    const char* e = std::getenv("FLOWMC_BT_PARTS");
+    return (e != nullptr && e[0] == '4') ? 4 : 2;
+  }();
+  switch (D.num_bins * 10 + parts) {
+    case 42: return launch_bt<4, 2>(D, PR, a, stream);
+    case 44: return launch_bt<4, 4>(D, PR, a, stream);
+    case 82: return launch_bt<8, 2>(D, PR, a, stream);
+    case 84: return launch_bt<8, 4>(D, PR, a, stream);
   }
   return FLOWMC_ERR_UNSUPPORTED;
 }

@@ -44,9 +44,10 @@
 
 namespace flowmc {
 
-// KIND_MALA_PT: MALA on the TEMPERED density beta_c * logpdf(x) + log_prior(x) with a per-chain inverse temperature
-// (ParallelTempering's individual steps, strategy/parallel_tempering.py:189-197; resource/logPDF.py:104-106)
-enum : int { KIND_MALA = 0, KIND_HMC = 1, KIND_GRW = 2, KIND_MALA_PT = 3 };
+// KIND_*_PT: the same kernel on the TEMPERED density beta_c * logpdf(x) + log_prior(x) with a per-chain inverse
+// temperature (ParallelTempering's individual steps with any ProposalBase, strategy/parallel_tempering.py:189-197;
+// resource/logPDF.py:104-106).  KIND % 3 is the proposal, KIND >= 3 the tempered variant.
+enum : int { KIND_MALA = 0, KIND_HMC = 1, KIND_GRW = 2, KIND_MALA_PT = 3, KIND_HMC_PT = 4, KIND_GRW_PT = 5 };
 
 constexpr int kChunk = 32;  // steps per key-schedule chunk (= one step per lane)
 
@@ -256,13 +257,18 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
   }
   __syncwarp();
   const typename T::Consts tc = T::prepare(a.data, d);
-  constexpr bool IS_MALA = KIND == KIND_MALA || KIND == KIND_MALA_PT;
-  constexpr bool TEMPERED = KIND == KIND_MALA_PT;
+  constexpr int BASE = KIND % 3;
+  constexpr bool IS_MALA = BASE == KIND_MALA, IS_HMC = BASE == KIND_HMC, IS_GRW = BASE == KIND_GRW;
+  constexpr bool TEMPERED = KIND >= KIND_MALA_PT;
   const float beta = (TEMPERED && a.beta != nullptr) ? a.beta[chain] : 1.0f;
-  // one evaluation of the (tempered) target at a point
+  // one evaluation of the (tempered) target at a point, with or without its gradient
   auto eval_grad = [&](const float (&xv)[DPL], float (&gv)[DPL]) -> float {
     if (TEMPERED) return eval_tempered<T, L, true>(tc, xv, gv, xrow, scratch, a.data, d, lg, beta, a.prior);
     return eval_target<T, L, true>(tc, xv, gv, xrow, scratch, a.data, d, lg);
+  };
+  auto eval_value = [&](const float (&xv)[DPL], float (&gv)[DPL]) -> float {
+    if (TEMPERED) return eval_tempered<T, L, false>(tc, xv, gv, xrow, scratch, a.data, d, lg, beta, a.prior);
+    return eval_target<T, L, false>(tc, xv, gv, xrow, scratch, a.data, d, lg);
   };
 
   Key kc;
@@ -279,8 +285,7 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
       g[k] = 0.0f;
     }
     // logpdf(initial_position) seeds the scan carry (take_steps.py:177); MALA/HMC cache the gradient
-    if (TEMPERED) lp = eval_grad(x, g);
-    else lp = eval_target<T, L, KIND != KIND_GRW>(tc, x, g, xrow, scratch, a.data, d, lg);
+    lp = IS_GRW ? eval_value(x, g) : eval_grad(x, g);
     // ProposalBase.kernel(): HMC and GRW use the caller-supplied log_prob (HMC.py:137,
     // Gaussian_random_walk.py:56); MALA ignores it and re-evaluates logpdf(position) (MALA.py:59,75,87)
     if (a.lp0 != nullptr && !IS_MALA) lp = a.lp0[chain];
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
   for (int k = 0; k < DPL; ++k) {
     cs[k] = 0.0f;
     ld[k] = 0.0f;
-    if (KIND == KIND_HMC) {
+    if (IS_HMC) {
       const int j = L::dim(k, lg);
       if (L::valid(j, d)) {
         cs[k] = a.hmc_colsum[j];
@@ -393,12 +398,12 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
           g[k] = acc ? g1[k] : g[k];
         }
         lp = acc ? lp1 : lp;
-      } else if (KIND == KIND_GRW) {
+      } else if (IS_GRW) {
         float prop[DPL], g1[DPL];
         draw_normals<L>(key1, d, lg, prop);
 #pragma unroll
         for (int k = 0; k < DPL; ++k) prop[k] = x[k] + prop[k] * dt;  // Gaussian_random_walk.py:49-52
-        const float lp1 = eval_target<T, L, false>(tc, prop, g1, xrow, scratch, a.data, d, lg);
+        const float lp1 = eval_value(prop, g1);
         acc = logu < (lp1 - lp);  // Gaussian_random_walk.py:56
 #pragma unroll
         for (int k = 0; k < DPL; ++k) x[k] = acc ? prop[k] : x[k];
@@ -448,7 +453,7 @@ __global__ void __launch_bounds__(32, MINB) local_steps_kernel(const LocalArgs a
           const float c1 = (it == a.n_leapfrog + 1) ? 0.5f : 1.0f;
 #pragma unroll
           for (int k = 0; k < DPL; ++k) xs[k] = xs[k] + (eps * 1.0f) * (p[k] * cs[k]);
-          lp1 = eval_target<T, L, true>(tc, xs, g1, xrow, scratch, a.data, d, lg);
+          lp1 = eval_grad(xs, g1);
 #pragma unroll
           for (int k = 0; k < DPL; ++k) p[k] = p[k] - (eps * c1) * (-g1[k]);
         }
@@ -727,6 +732,8 @@ int launch_local_steps(int kind, const LocalArgs* a, cudaStream_t stream) {
     case KIND_HMC: return launch_local_kind<T, KIND_HMC>(a, stream);
     case KIND_GRW: return launch_local_kind<T, KIND_GRW>(a, stream);
     case KIND_MALA_PT: return launch_local_kind<T, KIND_MALA_PT>(a, stream);
+    case KIND_HMC_PT: return launch_local_kind<T, KIND_HMC_PT>(a, stream);
+    case KIND_GRW_PT: return launch_local_kind<T, KIND_GRW_PT>(a, stream);
     default:
       flowmc_set_error("local_steps: unknown kernel kind");
       return -1;

@@ -99,6 +99,69 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// ---- distributed shared memory (DSMEM) between the CTAs of a cluster ----------------------------------
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(p)), "r"(rank));
+  return raddr;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t raddr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_cluster_f32(uint32_t raddr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_cluster_f32x4(uint32_t raddr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(raddr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+// Asynchronous remote store: writes v to `raddr` (a shared::cluster address of a peer CTA) and, when the write has been
+// performed, completes 4 bytes of the transaction count of the mbarrier at `rbar` (same CTA as raddr).  The receiver
+// only waits on its mbarrier: no release fence on the sending side, so the sender's outstanding GLOBAL stores are not
+// drained (a fence.acq_rel.cluster would wait for every one of them to reach L2).
+__device__ __forceinline__ void st_async_f32(uint32_t raddr, float v, uint32_t rbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr),
+               "r"(__float_as_uint(v)), "r"(rbar)
+               : "memory");
+}
+// Bulk copy from this CTA's shared memory into a peer CTA's (raddr, rbar: shared::cluster addresses from mapa_u32);
+// completes `bytes` on the peer's mbarrier.  bytes % 16 == 0, both addresses 16-byte aligned.  The source must have
+// been made visible to the async proxy (fence_proxy_async_smem) after the generic-proxy writes.
+__device__ __forceinline__ void bulk_s2peer(uint32_t raddr, const void* src_smem, uint32_t bytes, uint32_t rbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   raddr),
+               "r"(smem_u32(src_smem)), "r"(bytes), "r"(rbar)
+               : "memory");
+}
+// control-only arrival on a peer's mbarrier (no data is published through it)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// wait with acquire semantics at CLUSTER scope: remote st.shared::cluster writes released by the arriving threads of
+// other CTAs (mbar_arrive_remote) are visible afterwards
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (ok == 0);
+}
+
 // ---- TMEM -------------------------------------------------------------------------------------
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem) {  // one full warp

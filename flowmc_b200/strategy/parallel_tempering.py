@@ -5,10 +5,12 @@ pair of the tempered density, (2) one sweep of neighbour exchanges up the temper
 ``state.data["training"]``: store the tempered positions and adapt the temperatures from the exchange acceptance.
 
 On the B200 path (1) is ONE launch of the persistent local-step kernel over ``n_chains * n_temps`` virtual chains
-(``flowmc_local_steps(FLOWMC_KERNEL_MALA_TEMPERED)``: per-chain inverse temperature, prior evaluated in the kernel,
-explicit per-(chain, temperature) keys ``split(split(subkey, n_chains)[c], n_temps)[t]``), (2) is ``flowmc_pt_exchange``
-(one thread per chain walks the ladder), and (3) is the reference's arithmetic on ``n_temps`` numbers on the host.
-Only MALA is wired up as the tempered kernel (the reference's PT bundle uses MALA, RQSpline_MALA_PT.py).
+(``flowmc_local_steps(FLOWMC_KERNEL_{MALA,HMC,GRW}_TEMPERED)``: per-chain inverse temperature, prior evaluated in the
+kernel, explicit per-(chain, temperature) keys ``split(split(subkey, n_chains)[c], n_temps)[t]``), (2) is
+``flowmc_pt_exchange`` (one thread per chain walks the ladder), and (3) is the reference's arithmetic on ``n_temps``
+numbers on the host.  Any of the three local kernels can be the tempered kernel, as in the reference, which hands
+whatever ``ProposalBase`` the resources name to ``_individual_step`` (parallel_tempering.py:74,135-289; its PT bundle
+uses MALA, RQSpline_MALA_PT.py).
 """
 from __future__ import annotations
 
@@ -20,14 +22,13 @@ import torch
 from .. import random as frandom
 from .._lib import LocalParams, check, lib
 from ..resource.buffers import Buffer
-from ..resource.kernel.MALA import MALA
-from ..resource.kernel.base import ProposalBase
+from ..resource.kernel.base import LocalKernel, ProposalBase
 from ..resource.logPDF import TemperedPDF
 from ..resource.states import State
 from .base import Strategy
 
 _u32p = C.POINTER(C.c_uint32)
-_KERNEL_MALA_TEMPERED = 3
+_TEMPERED_KIND_OFFSET = 3      # FLOWMC_KERNEL_{MALA,HMC,GRW}_TEMPERED = 3 + the plain kind
 
 
 class ParallelTempering(Strategy):
@@ -84,8 +85,9 @@ class ParallelTempering(Strategy):
     def _ensemble_steps(self, kernel, subkey, positions, logpdf: TemperedPDF, temperatures, data):
         """``subkey``: the key whose ``split(subkey, n_chains)`` the reference vmaps over.  Returns the final positions
         [n_chains, n_temps, d], final tempered log-probs [n_chains, n_temps], accept flags [n_chains, n_temps, n_steps]."""
-        if not isinstance(kernel, MALA):
-            raise NotImplementedError("flowmc_b200 ParallelTempering runs MALA as the tempered kernel")
+        if not isinstance(kernel, LocalKernel) or kernel.KIND not in (0, 1, 2):
+            raise NotImplementedError("flowmc_b200 ParallelTempering runs MALA, HMC or GaussianRandomWalk as the tempered "
+                                      "kernel")
         n, n_temps, d = positions.shape
         dev = positions.device
         offset, n_glob = self.chain_shard if self.chain_shard is not None else (0, n)
@@ -102,9 +104,7 @@ class ParallelTempering(Strategy):
         lp = torch.empty((nv, T_), dtype=torch.float32, device=dev)
         acc = torch.empty((nv, T_), dtype=torch.float32, device=dev)
         last = torch.empty((nv, d), dtype=torch.float32, device=dev)
-        p = LocalParams()
-        p.step_size = float(kernel.step_size)
-        p.layout_hint = int(getattr(kernel, "layout_hint", 0))
+        p, keep = kernel._local_params(d, dev)           # step size, HMC mass constants, layout hint
         p.chain_keys = keys_d.data_ptr()
         p.beta = beta.data_ptr()
         prior_d = None
@@ -115,7 +115,7 @@ class ParallelTempering(Strategy):
         dummy_key = np.zeros(2, np.uint32)
         key_out = np.zeros(2, np.uint32)
         with torch.cuda.device(dev):
-            check(lib.flowmc_local_steps(_KERNEL_MALA_TEMPERED, logpdf.target.target_id, pk.data_ptr(),
+            check(lib.flowmc_local_steps(_TEMPERED_KIND_OFFSET + kernel.KIND, logpdf.target.target_id, pk.data_ptr(),
                                          dummy_key.ctypes.data_as(_u32p), x0.data_ptr(), pos.data_ptr(), lp.data_ptr(),
                                          acc.data_ptr(), T_, 0, nv, d, T_, 1, 0, nv, C.byref(p),
                                          key_out.ctypes.data_as(_u32p), last.data_ptr(),

@@ -49,6 +49,8 @@ extern "C" {
 #define FLOWMC_KERNEL_HMC 1
 #define FLOWMC_KERNEL_GRW 2
 #define FLOWMC_KERNEL_MALA_TEMPERED 3 /* MALA on beta_c * logpdf + log_prior (ParallelTempering) */
+#define FLOWMC_KERNEL_HMC_TEMPERED 4  /* HMC on the tempered density */
+#define FLOWMC_KERNEL_GRW_TEMPERED 5  /* Gaussian random walk on the tempered density */
 
 /* error codes */
 #define FLOWMC_OK 0
@@ -101,8 +103,8 @@ typedef struct FlowmcLocalParams {
   const uint32_t* chain_keys; /* optional, device [n_chains,2]: the chains' initial keys; NULL = split(subkey,
                                * n_chains_global)[global chain index] (take_steps.py:72).  ParallelTempering passes
                                * split(split(subkey, n_chains)[c], n_temps)[t] (parallel_tempering.py:289-293) */
-  const float* beta;      /* FLOWMC_KERNEL_MALA_TEMPERED: device [n_chains] inverse temperatures 1 / T (NULL = 1) */
-  const float* prior;     /* FLOWMC_KERNEL_MALA_TEMPERED: device [4, d] = c, m, lo, hi of
+  const float* beta;      /* FLOWMC_KERNEL_*_TEMPERED: device [n_chains] inverse temperatures 1 / T (NULL = 1) */
+  const float* prior;     /* FLOWMC_KERNEL_*_TEMPERED: device [4, d] = c, m, lo, hi of
                            * log_prior(x) = -sum_j c_j (x_j - m_j)^2 inside [lo, hi], -inf outside; NULL = flat 0 */
   int force_n_seg;        /* time slicing: <= 0 = one launch for the whole call (default: measured fastest on B200,
                            * profiles/r02_slice_sweep.jsonl); > 1 = cut the n_steps into this many segments that run

@@ -1,5 +1,6 @@
 """CPU restatement (TEST INFRASTRUCTURE ONLY) of ParallelTempering, src/flowMC/strategy/parallel_tempering.py:47-436,
-and TemperedPDF.tempered_log_pdf, src/flowMC/resource/logPDF.py:104-106, with MALA as the tempered kernel.
+and TemperedPDF.tempered_log_pdf, src/flowMC/resource/logPDF.py:104-106, with MALA (what the reference's PT bundle
+uses), HMC or the Gaussian random walk as the tempered kernel (the reference passes any ProposalBase, :74,135-289).
 numpy float32; the (chain, temperature) pairs are flattened into rows.  Parity unpinned against the reference's own
 outputs (jax is not installable here); the invariants the reference tests assert are checked in
 tests/test_oracle_golden.py."""
@@ -36,7 +37,7 @@ class _Tempered:
 
 
 def ensemble_steps(subkey, positions, target, data, temperatures, n_steps, step_size, prior=None,
-                   chain_offset=0, n_chains_total=None):
+                   chain_offset=0, n_chains_total=None, kind="MALA", **kernel_kw):
     """_ensemble_step vmapped over chains (:91-101, :250-290).  positions [n, n_temps, d].  Returns final positions,
     final TEMPERED log-probs [n, n_temps], accept flags [n, n_temps, n_steps]."""
     positions = np.asarray(positions, F32)
@@ -47,6 +48,7 @@ def ensemble_steps(subkey, positions, target, data, temperatures, n_steps, step_
     beta = np.tile((F32(1.0) / np.asarray(temperatures, F32)).astype(F32), n)      # logPDF.py:106
     tgt = _Tempered(target, beta, prior)
     local.TARGETS[tgt.name] = tgt
+    kernel = local.make_kernel(kind, step_size=step_size, **kernel_kw)
     try:
         x = positions.reshape(n * n_temps, d).copy()
         lp, _ = tgt.logp_grad(x, data)                                             # :229-231
@@ -54,7 +56,7 @@ def ensemble_steps(subkey, positions, target, data, temperatures, n_steps, step_
         for t in range(n_steps):                                                   # _individual_step_body (:189-197)
             s = rng.split(keys, 2)
             keys, sub = s[:, 0, :], s[:, 1, :]
-            x, lp, acc, _ = local.mala_kernel(sub, x, lp, tgt.name, data, step_size)
+            x, lp, acc, _ = kernel(sub, x, lp, tgt.name, data)
             accs[:, t] = acc
     finally:
         del local.TARGETS[tgt.name]
@@ -100,13 +102,14 @@ def adapt_temperature(temperatures, do_accept):
 
 
 def parallel_tempering(rng_key, initial_position, tempered_positions, temperatures, target, data, n_steps, step_size,
-                       prior=None, training=True):
+                       prior=None, training=True, kind="MALA", **kernel_kw):
     """ParallelTempering.__call__ (:47-132).  Returns (rng_key, positions[:, 0], new tempered positions, new
     temperatures, exchange accepts)."""
     rng_key, _ = rng.split(rng_key)                                                # :73
     positions = np.concatenate([np.asarray(initial_position, F32)[:, None, :], np.asarray(tempered_positions, F32)], axis=1)
     rng_key, subkey = rng.split(rng_key)
-    positions, _, _ = ensemble_steps(subkey, positions, target, data, temperatures, n_steps, step_size, prior)
+    positions, _, _ = ensemble_steps(subkey, positions, target, data, temperatures, n_steps, step_size, prior,
+                                     kind=kind, **kernel_kw)
     rng_key, subkey = rng.split(rng_key)
     positions, _, accs, _, _ = exchange(subkey, positions, target, data, temperatures)
     temps = np.asarray(temperatures, F32)

@@ -1,5 +1,5 @@
 """Pipeline timeline of CTA 0 of the tensor-core flow kernel (clock64 stamps) for one log_prob launch
-(python scripts/tc_timeline.py [c4|c5] [terms] [train]: the training forward of one loss_and_grad call)."""
+(python scripts/tc_timeline.py [c4|c5] [terms] [train] [rows]: the training forward of one loss_and_grad call)."""
 import sys
 sys.path.insert(0, "/root/repo")
 import torch
@@ -12,7 +12,8 @@ terms = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 m = MaskedCouplingRQSpline(d, L, [128, 128], 8, frandom.PRNGKey(1))
 m.tc_terms = terms
 train = len(sys.argv) > 3 and sys.argv[3] == "train"
-x = frandom.normal(frandom.PRNGKey(2), ((128 if train else 148) * 128, d))
+rows = int(sys.argv[4]) if len(sys.argv) > 4 else (128 if train else 148) * 128
+x = frandom.normal(frandom.PRNGKey(2), (rows, d))
 run = (lambda: m.loss_and_grad(x)) if train else (lambda: m.log_prob(x))
 run()
 buf = torch.zeros(4 * 256, dtype=torch.int64, device="cuda")
@@ -26,4 +27,4 @@ for role, name in enumerate(("producer (stage slot free -> copy issued)", "mma (
                              "epilogue thread 0")):
     v = t[role][t[role] > 0] - t0
     print(name, len(v))
-    print(" ", " ".join(str(int(c)) for c in v[:80]))
+    print(" ", " ".join(str(int(c)) for c in v[:120]))

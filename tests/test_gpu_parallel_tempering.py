@@ -148,16 +148,67 @@ class TestTemperingStrategies:
             _, _, part = strat2(k2, res2, x02[a:b], self._data())
             assert torch.equal(part, full[a:b])
 
-    def test_only_mala_and_device_priors(self, cuda):
+    def test_only_local_kernels_and_device_priors(self, cuda):
         from flowmc_b200 import targets as T
-        from flowmc_b200.resource.kernel.Gaussian_random_walk import GaussianRandomWalk
+        from flowmc_b200.resource.kernel.NF_proposal import NFProposal
         from flowmc_b200.resource.logPDF import TemperedPDF
+        from flowmc_b200.resource.model.nf_model.rqSpline import MaskedCouplingRQSpline
         with pytest.raises(TypeError):
             TemperedPDF(T.iso_gaussian(0.5, "data"), lambda x, data: 0.0, n_dims=3)
         key, resources, strat, x0 = self.initialize()
-        resources["MALA"] = GaussianRandomWalk(0.1)
+        resources["MALA"] = NFProposal(MaskedCouplingRQSpline(3, 2, [16, 16], 8, key))
         with pytest.raises(NotImplementedError):
             strat(key, resources, x0, self._data())
+
+    @pytest.mark.parametrize("kind", ["HMC", "GRW"])
+    @pytest.mark.parametrize("with_prior", [False, True])
+    def test_any_local_kernel_as_the_tempered_kernel(self, cuda, kind, with_prior):
+        """The reference hands whatever ProposalBase the resources name to _individual_step
+        (parallel_tempering.py:74,135-289): HMC (dense inverse mass) and the Gaussian random walk on the tempered
+        density, against the oracle -- ensemble steps and one full ParallelTempering call."""
+        from flowmc_b200 import random as frandom
+        from flowmc_b200.resource.kernel.Gaussian_random_walk import GaussianRandomWalk
+        from flowmc_b200.resource.kernel.HMC import HMC
+        from flowmc_b200.resource.logPDF import BoxQuadraticPrior
+        from oracle import parallel_tempering as opt, targets as O
+        d = 5
+        prior = BoxQuadraticPrior(c=0.05, mean=0.5, lower=-6.0, upper=6.0) if with_prior else None
+        key, resources, strat, x0 = self.initialize(prior=prior, n_chains=33, n_dims=d, training=True)
+        if kind == "HMC":
+            rs = np.random.RandomState(2)
+            A = rs.randn(d, d) * 0.2
+            M = (A @ A.T + np.eye(d)).astype(np.float32)
+            resources["MALA"] = HMC(M, 0.3, 3)
+            okw = dict(kind="HMC", n_leapfrog=3, condition_matrix=M)
+            step = 0.3
+        else:
+            resources["MALA"] = GaussianRandomWalk(0.6)
+            okw = dict(kind="GRW")
+            step = 0.6
+        strat.n_steps = 7
+        positions = torch.cat([x0[:, None, :], resources["tempered_positions"].data], dim=1)
+        temps = resources["temperatures"].data
+        k1, subkey = frandom.split(key)
+        pos, lp, acc = strat._ensemble_steps(resources["MALA"], subkey, positions, resources["logpdf"], temps,
+                                             self._data(d))
+        packed = O.IsoGaussian.pack(d, 0.5, np.arange(d))
+        o_pos, o_lp, o_acc = opt.ensemble_steps(subkey, positions.cpu().numpy(), "iso_gaussian", packed,
+                                                temps.cpu().numpy(), 7, step, prior=_prior_array(prior, d), **okw)
+        same = (acc.cpu().numpy() == o_acc).all(axis=2)
+        assert same.mean() > 0.9, f"tempered {kind} accept flags diverge from the oracle"
+        assert 0.05 < float(acc.mean()) < 1.0
+        assert_close(pos.cpu().numpy()[same], o_pos[same], "positions", rtol=3e-4)
+        assert_close(lp.cpu().numpy()[same], o_lp[same], "tempered log-probs", rtol=3e-4)
+        # one full call: keys, cold-chain positions, adapted ladder
+        tp0 = resources["tempered_positions"].data.cpu().numpy().copy()
+        new_key, res, cold = strat(key, resources, x0, self._data(d))
+        o_key, o_cold, o_tp, o_t, o_acc2 = opt.parallel_tempering(key, x0.cpu().numpy(), tp0, temps.cpu().numpy(),
+                                                                  "iso_gaussian", packed, 7, step,
+                                                                  prior=_prior_array(prior, d), training=True, **okw)
+        assert np.array_equal(new_key, o_key)
+        agree = np.abs(cold.cpu().numpy() - o_cold).max(axis=1) <= 3e-4 * max(1.0, float(np.abs(o_cold).max()))
+        assert agree.mean() > 0.85          # chains whose accept / swap decisions all agree land on the same point
+        np.testing.assert_allclose(res["temperatures"].data.cpu().numpy(), o_t, rtol=0.2)
 
 
 def test_rqspline_mala_pt_bundle(cuda):
