@@ -934,6 +934,11 @@ static size_t tc_split_smem_bytes(const FlowmcFlowDesc& D) {
 // co-resident clusters of R CTAs of the split training-forward kernel on this device (0 = unknown yet)
 static int g_split_max_clusters[9] = {0};
 
+// the backward kernel reports how many of ITS clusters are co-resident: the split factor honours the smaller number
+void tc_split_note_max_clusters(int R, int n) {
+  if (R >= 2 && R <= 8 && n > 0 && (g_split_max_clusters[R] == 0 || n < g_split_max_clusters[R])) g_split_max_clusters[R] = n;
+}
+
 // Feature split of the training forward pass: clusters of R CTAs per tile (see the kernel).  Returns the cluster size
 // to use (1 = not applicable: the caller runs the one-CTA-per-tile kernel).
 int tc_split_factor(const FlowmcFlowDesc& D, int64_t tiles) {

@@ -60,6 +60,7 @@ int flow_transform(const FlowmcFlowDesc& D, bool inverse, const float* P, const 
 // tensor-core path (flow_tc.cu)
 bool flow_tc_enabled(const FlowmcFlowDesc& D);
 int tc_split_factor(const FlowmcFlowDesc& D, int64_t tiles);  // cluster size of the feature-split training kernels
+void tc_split_note_max_clusters(int R, int n);
 int flow_transform_tc(const FlowmcFlowDesc& D, bool inverse, const float* P, const float* x, int64_t n, float* y,
                       float* ld, int pre, int post, const uint32_t* keys, Key hk, int64_t rpk, cudaStream_t stream,
                       const int32_t* idx, float* save_x = nullptr, float* save_h = nullptr,

@@ -151,6 +151,7 @@ struct BtArgs {
   int64_t pstride;     // floats per CTA: L * layer_stride + 4 (the last 4: loss partial)
   int64_t n_tiles;
   long long* timing;  // optional diagnostics: clock64 stamps of epilogue thread 0 of CTA 0
+  int split_r;        // feature split: CTAs per tile (cluster size), 1 = one CTA per tile
   int n_cta;          // CTAs that process tiles; CTAs beyond them (if any) are REDUCERS, see bt_reduce_layer
   int* done;          // [L] tile CTAs that have finished layer l (reducer hand-off) + [1] reduction work counter;
                       // zeroed by bt_pack_kernel
@@ -163,7 +164,7 @@ struct BtArgs {
 
 __device__ __forceinline__ void bt_reduce_layer(const FlowmcFlowDesc& D, const float* partial, int64_t pstride,
                                                 int n_cta, float* __restrict__ grad, int l, int g0, int gstep,
-                                                int g_end);
+                                                int g_end, int R = 1, int fc = 1);
 __device__ __forceinline__ float bt_reduce_loss(const float* partial, int64_t pstride, int n_cta);
 
 // PARTS = epilogue threads per sample row: 2 (default) or 4 (16 epilogue warps, 576 threads, 96 registers per thread:
@@ -172,6 +173,8 @@ template <int PARTS>
 struct BtSmem {
   uint64_t stage_full[BT_STAGES], stage_empty[BT_STAGES], acc_full;
   uint64_t a_ready[4];  // per K-chunk (32 columns) of the A operand, one arrival per epilogue warp
+  uint64_t xbar[2];  // feature split: the two exchange rounds of finish_layer (one arrival per epilogue warp of
+                     // every CTA of the cluster)
   uint32_t tmem_base;
   float red[2 * 4 * PARTS];
   float bsum[PARTS][TC_M];
@@ -180,10 +183,25 @@ struct BtSmem {
 template <int N>
 __device__ __forceinline__ void bt_bar() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
-template <int KB, int PARTS>
+// SPLIT: a cluster of R = a.split_r CTAs shares ONE tile, like the split training forward (flow_tc.cu).  Every CTA takes
+// the spline chunks with index % R == its cluster rank; the data gradient it accumulates (dh_last) is therefore only a
+// PARTIAL sum -- and stays one: the tanh units are linear in it, so every CTA pushes its partial through them and
+// stores partial weight gradients (the accumulator reduction sums them like it sums tiles).  What the CTAs must
+// exchange per layer is small: the gradient w.r.t. the layer input -- for the transformed features the owner's value,
+// for the conditioning features the sum of the CTAs' partials -- pulled through distributed shared memory in
+// finish_layer (two cluster rounds, partials added in rank order: deterministic).
+template <int KB, int PARTS, bool SPLIT = false>
 __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kernel(const FlowmcFlowDesc D,
                                                                                  const BtProgram PR, const BtArgs a) {
   constexpr int NP = 3 * KB + 1;
+  const uint32_t R = SPLIT ? (uint32_t)a.split_r : 1u;
+  const uint32_t crank = SPLIT ? tc::cluster_rank() : 0u;
+  const int64_t tile_first = SPLIT ? (int64_t)(blockIdx.x / R) : (int64_t)blockIdx.x;
+  const int64_t tile_step = SPLIT ? (int64_t)(a.n_cta / (int)R) : (int64_t)a.n_cta;
+  // items 2c, 2c + 1 (c < number of chunks) are the data / weight gradient GEMMs of spline chunk c
+  auto skip_item = [&](const BtItem& it, int ii) -> bool {
+    return SPLIT && (it.kind == BK_DG3 || it.kind == BK_WG3) && (uint32_t)(ii >> 1) % R != crank;
+  };
   constexpr int EPI_WARPS = 4 * PARTS, EPI = EPI_WARPS * 32;
   constexpr int CPT = 128 / PARTS;  // accumulator / operand columns per epilogue thread of a row
   auto epi_bar = [] { bt_bar<EPI>(); };
@@ -209,11 +227,13 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
     }
     tc::mbar_init(&S->acc_full, 1);
     for (int i = 0; i < 4; ++i) tc::mbar_init(&S->a_ready[i], EPI_WARPS);
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&S->xbar[i], R * EPI_WARPS);
     tc::fence_mbar_init();
   }
   if (warp == EPI_WARPS) tc::tmem_alloc<512>(&S->tmem_base);
   tc::tc_fence_before();
   __syncthreads();
+  if (SPLIT) tc::cluster_sync();  // every CTA's barriers exist before a peer arrives on them
   tc::tc_fence_after();
   const uint32_t tbase = S->tmem_base;
   const uint32_t t_ahi = tbase, t_alo = tbase + 128;
@@ -221,13 +241,14 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
   if (warp == EPI_WARPS) {
     // ===== B-stage producer ====================================================================
     uint32_t s = 0, ph = 0;
-    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += a.n_cta)
+    for (int64_t tile = tile_first; tile < a.n_tiles; tile += tile_step)
     for (int l = L - 1; l >= 0; --l) {
       const int p = l & 1;
       const uint8_t* wbase = a.wimg + bt_layer_base(PR, l);
       const uint8_t* abase = a.act_img + (tile * L + l) * tc_act_layer_bytes(D);
       for (int ii = 0; ii < PR.n_items[p]; ++ii) {
         const BtItem it = PR.items[p][ii];
+        if (skip_item(it, ii)) continue;
         const uint32_t bytes = 2u * it.N * 128u;
         const uint8_t* src = (it.act ? abase : wbase) + it.off;
         for (int kc = 0; kc < it.n_kc; ++kc) {
@@ -244,16 +265,19 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
   } else if (warp == EPI_WARPS + 1) {
     // ===== MMA issuer ==========================================================================
     uint32_t s = 0, ph = 0, a_ph = 0;
-    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += a.n_cta)
+    for (int64_t tile = tile_first; tile < a.n_tiles; tile += tile_step)
     for (int l = L - 1; l >= 0; --l) {
       const int p = l & 1;
+      bool first_chunk = true;  // the first spline chunk THIS CTA runs in the layer starts dh_last afresh
       for (int ii = 0; ii < PR.n_items[p]; ++ii) {
         const BtItem it = PR.items[p][ii];
+        if (skip_item(it, ii)) continue;
         // (the epilogue signals the item's A operand K-chunk by K-chunk, see below)
         const bool wg = (it.kind == BK_WG3) || (it.kind == BK_WGH);
         const uint32_t t_acc = tbase + (wg ? 384 : 256);
         const uint32_t idesc = tc::make_idesc_tf32(TC_M, it.N);
-        const bool cont = (it.kind == BK_DG3) && (it.lin > 0);  // later chunks accumulate into dh_last
+        const bool cont = (it.kind == BK_DG3) && !first_chunk;  // later chunks accumulate into dh_last
+        if (it.kind == BK_DG3) first_chunk = false;
         for (int kc = 0; kc < it.n_kc; ++kc) {
           tc::mbar_wait(&S->a_ready[kc], (a_ph >> kc) & 1);  // K-chunk kc of the A operand is written
           a_ph ^= 1u << kc;
@@ -319,6 +343,22 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
       f_ph ^= 1;
       tc::tc_fence_after();
     };
+    // feature split: this thread's column of the exchange buffer T[.][t] in every CTA of the cluster; a control round =
+    // release my shared-memory writes at cluster scope, arrive on every CTA's barrier, wait (acquire) for mine
+    uint32_t t_remote[8];
+    uint32_t x_ph[2] = {0, 0};
+    if (SPLIT) {
+#pragma unroll
+      for (uint32_t k = 0; k < 8; ++k) t_remote[k] = tc::mapa_u32(T + t, k < R ? k : 0u);
+    }
+    auto cluster_round = [&](int k) {
+      tc::fence_cluster();
+      __syncwarp();
+      if (lane == 0)
+        for (uint32_t rk = 0; rk < R; ++rk) tc::mbar_arrive_remote(&S->xbar[k], rk);
+      tc::mbar_wait_cluster(&S->xbar[k], x_ph[k]);
+      x_ph[k] ^= 1;
+    };
     // 8 consecutive A columns of this thread's row, from registers
     auto write_a8 = [&](int col, const float* v) {
       uint32_t hi[8], lo[8];
@@ -327,9 +367,9 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
       tc::tmem_st8(t_ahi + lane_base + col, hi);
       tc::tmem_st8(t_alo + lane_base + col, lo);
     };
-    for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += a.n_cta) {
-    const bool first = tile == (int64_t)blockIdx.x;  // first tile of this CTA: store, later tiles: accumulate
-    const bool last = tile + a.n_cta >= a.n_tiles;   // last tile: publish the layers to the reducers
+    for (int64_t tile = tile_first; tile < a.n_tiles; tile += tile_step) {
+    const bool first = tile == tile_first;           // first tile of this CTA: store, later tiles: accumulate
+    const bool last = tile + tile_step >= a.n_tiles; // last tile: publish the layers to the reducers
     auto acc_to = [&](float* ptr, float v) { *ptr = first ? v : *ptr + v; };
     auto store4 = [&](float* ptr, const float* v) {
       float4 w = make_float4(v[0], v[1], v[2], v[3]);
@@ -357,7 +397,8 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
       gr[j] = valid ? a.inv_n * (y - P[D.off_base_mean + j]) / P[D.off_base_cov + (int64_t)j * d + j] : 0.0f;
     }
     epi_bar();
-    if (tid == 0) acc_to(PB + a.pstride - 4, (S->red[0] + S->red[1]) + (S->red[2] + S->red[3]));
+    if (tid == 0)  // (split: every CTA of the cluster sees the same rows; rank 0 accounts for them)
+      acc_to(PB + a.pstride - 4, crank == 0 ? (S->red[0] + S->red[1]) + (S->red[2] + S->red[3]) : 0.0f);
 
     // dY of the unit (layer l, items ii / ii + 1): into the transpose buffer T[column][row] (for the weight-gradient
     // operand) AND, straight from the registers, into the A region (lane = this row) for the data-gradient GEMM.
@@ -457,12 +498,14 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
     // into L2 one unit ahead
     auto prefetch_next = [&](int l, int ii) {
       int nl = l, nii = ii + 2;
+      while (nii < PR.n_items[l & 1] && skip_item(PR.items[l & 1][nii], nii)) nii += 2;
       if (nii >= PR.n_items[l & 1]) {
         // last unit of layer l: finish_layer(l) will read this row's layer input (its share of the d columns)
         const float* xin = a.save_x + ((int64_t)l * n + r) * d;
         for (int j = j_lo; j < j_hi; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(xin + j));
         --nl;
         nii = 0;
+        while (nl >= 0 && nii < PR.n_items[nl & 1] && skip_item(PR.items[nl & 1][nii], nii)) nii += 2;
       }
       if (nl < 0) return;
       const BtItem it = PR.items[nl & 1][nii];
@@ -543,6 +586,42 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
       const float shift = PL[D.off_shift], e = expf(PL[D.off_scale]);
       const float* xin = a.save_x + ((int64_t)l * n + r) * d;
       float ssc = 0.0f, ssh = 0.0f;
+      if (SPLIT) {
+        // Exchange buffer X[j][row] = T (free here: the last unit's transposed reads are behind an epi_bar).  Every CTA
+        // publishes, for its share of the columns: conditioning feature j -> ITS partial of the conditioner-input
+        // gradient (acc 0); transformed feature j it owns -> the spline adjoint's dL/dx (already in gr[j]).
+        const int fc = PR.items[l & 1][0].n_feat;  // features per (full) chunk
+        for (int c = (j_lo / 16) * 16; c < j_hi; c += 16) {
+          float v[16];
+          tc::tmem_ld16(tbase + 256 + lane_base + c, v);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int j = c + u;
+            if (j >= j_lo && j < j_hi) T[j * BT_TS + t] = (((j + l) & 1) == 1) ? v[u] : gr[j];
+          }
+        }
+        cluster_round(0);  // every CTA's contributions are in its T
+        for (int j = j_lo; j < j_hi; ++j) {
+          float ga;
+          if (((j + l) & 1) == 1) {  // conditioning: dL/dy_j + the sum of the CTAs' partials, in rank order
+            float tot = 0.0f;
+            for (uint32_t k = 0; k < R; ++k)
+              tot += (k == crank) ? T[j * BT_TS + t] : tc::ld_cluster_f32(t_remote[k] + 4u * (uint32_t)(j * BT_TS));
+            ga = gr[j] + tot;
+          } else {                   // transformed: the owner's dL/dx
+            const uint32_t own = (uint32_t)(((j - (l & 1)) >> 1) / fc) % R;
+            ga = (own == crank) ? gr[j] : tc::ld_cluster_f32(t_remote[own] + 4u * (uint32_t)(j * BT_TS));
+          }
+          const float xa = (xin[j] + shift) * e;
+          if (valid) {
+            ssc += ga * xa;
+            ssh += ga * e;
+          }
+          gr[j] = ga * e;
+        }
+        cluster_round(1);  // every CTA has read what it needs: T may be rewritten by the next unit
+      } else
       for (int c = (j_lo / 16) * 16; c < j_hi; c += 16) {
         float v[16];
         tc::tmem_ld16(tbase + 256 + lane_base + c, v);  // N = pad16(d) columns
@@ -579,8 +658,9 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
           sb += S->red[EPI_WARPS + w];
         }
         const int n_valid = (int)min((int64_t)TC_M, n - row0);
-        acc_to(GL + D.off_scale, sa - a.inv_n * (float)d * (float)n_valid);
-        acc_to(GL + D.off_shift, sb);
+        // (split: every CTA of the cluster computed the same sums from the exchanged gradient; rank 0 accounts for them)
+        acc_to(GL + D.off_scale, crank == 0 ? sa - a.inv_n * (float)d * (float)n_valid : 0.0f);
+        acc_to(GL + D.off_shift, crank == 0 ? sb : 0.0f);
       }
       epi_bar();  // gr complete for the next layer
     };
@@ -588,6 +668,7 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
     // One loop, one call site per stage; the iteration after the last unit only drains: it finishes the last
     // layer and stores the last dW tile.
     int l = L - 1, ii = 0, pl = -1, pii = 0;  // current unit; previous unit (its dW tile is still in acc 1)
+    while (ii < PR.n_items[l & 1] && skip_item(PR.items[l & 1][ii], ii)) ii += 2;  // split: the first unit this CTA owns
     int pending_pub = -1;                     // layer whose accumulator is complete but not yet published
     while (true) {
       const bool have = l >= 0;
@@ -648,15 +729,18 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
       pl = l;
       pii = ii;
       ii += 2;
+      while (ii < PR.n_items[l & 1] && skip_item(PR.items[l & 1][ii], ii)) ii += 2;
       if (ii >= PR.n_items[l & 1]) {
         --l;
         ii = 0;
+        while (l >= 0 && ii < PR.n_items[l & 1] && skip_item(PR.items[l & 1][ii], ii)) ii += 2;
       }
     }
     }  // tiles
     tc::tc_fence_before();
   }
   __syncthreads();
+  if (SPLIT) tc::cluster_sync();  // no CTA leaves while a peer may still read its shared memory / arrive on its barriers
   tc::tc_fence_after();
   if (warp == EPI_WARPS) tc::tmem_dealloc<512>(tbase);
   }  // tile CTA
@@ -705,9 +789,12 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
 // canonical row).  Entries no CTA writes (alignment padding, W3 / b3 rows of the features a layer does not
 // transform, W1 columns of the masked inputs) are recognised from the index and left at zero.
 // Reduces the groups g = g0, g0 + gstep, ... < g_end of layer l.
+// Feature split (R > 1 CTAs per tile, accumulator index = cluster * R + rank): the rows of W3 / b3 that belong to
+// spline chunk c were written only by rank c % R of every cluster (fc = features per chunk); everything else holds a
+// partial (or zero) in every accumulator.
 __device__ __forceinline__ void bt_reduce_layer(const FlowmcFlowDesc& D, const float* partial, int64_t pstride,
                                                 int n_cta, float* __restrict__ grad, int l, int g0, int gstep,
-                                                int g_end) {
+                                                int g_end, int R, int fc) {
   const int nh = D.n_linear - 1, NP = 3 * D.num_bins + 1, d = D.n_features;
   const int H = D.dims[nh];
   const bool w0_permuted = (d & 3) == 0;
@@ -715,12 +802,14 @@ __device__ __forceinline__ void bt_reduce_layer(const FlowmcFlowDesc& D, const f
     const int64_t jo = (int64_t)g * 4;  // private offset inside the layer
     int64_t o = jo;                     // canonical offset of the group's first element
     bool live[4] = {false, false, false, false};
+    int owner[4] = {-1, -1, -1, -1};    // feature split: the only rank that wrote the element (-1: all ranks did)
     if (jo >= D.off_W[nh] && jo < D.off_W[nh] + (int64_t)D.dims[nh + 1] * H) {
       const int jj = (int)(jo - D.off_W[nh]);
       const int f = jj / (NP * H), r2 = jj - f * NP * H;
       const int c = (r2 / (4 * NP)) * 4, rr = (r2 >> 2) % NP;
       o = D.off_W[nh] + (int64_t)(f * NP + rr) * H + c;
       live[0] = live[1] = live[2] = live[3] = ((f ^ l) & 1) == 0;
+      if (R > 1) owner[0] = owner[1] = owner[2] = owner[3] = (((f - (l & 1)) >> 1) / fc) % R;
     } else if (jo >= D.off_W[0] && jo < D.off_W[0] + (int64_t)D.dims[1] * d) {
       if (w0_permuted) {
         const int jj = (int)(jo - D.off_W[0]), N = D.dims[1];
@@ -749,7 +838,9 @@ __device__ __forceinline__ void bt_reduce_layer(const FlowmcFlowDesc& D, const f
         for (int e = 0; e < 4; ++e) {
           const int64_t oe = jo + e;
           if (oe >= D.off_b[nh] && oe < D.off_b[nh] + D.dims[nh + 1]) {
-            live[e] = ((((int)(oe - D.off_b[nh]) / NP) ^ l) & 1) == 0;
+            const int f = (int)(oe - D.off_b[nh]) / NP;
+            live[e] = ((f ^ l) & 1) == 0;
+            if (R > 1 && live[e]) owner[e] = (((f - (l & 1)) >> 1) / fc) % R;
           } else if (oe == D.off_scale || oe == D.off_shift) {
             live[e] = true;
           } else {
@@ -759,7 +850,32 @@ __device__ __forceinline__ void bt_reduce_layer(const FlowmcFlowDesc& D, const f
         }
       }
     }
-    if (live[0] | live[1] | live[2] | live[3]) {
+    if (R > 1 && (owner[0] >= 0 || owner[1] >= 0 || owner[2] >= 0 || owner[3] >= 0)) {
+      // owner-written elements: sum over the clusters, reading the owning rank's accumulator of each
+      const float* base = partial + (int64_t)l * D.layer_stride + jo;
+      float sv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      const int n_cl = n_cta / R;
+      if (owner[0] == owner[1] && owner[0] == owner[2] && owner[0] == owner[3]) {
+        for (int cl = 0; cl < n_cl; ++cl) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(base + (int64_t)(cl * R + owner[0]) * pstride));
+          sv[0] += v.x; sv[1] += v.y; sv[2] += v.z; sv[3] += v.w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (!live[e]) continue;
+          if (owner[e] >= 0) {
+            for (int cl = 0; cl < n_cl; ++cl) sv[e] += __ldcg(base + (int64_t)(cl * R + owner[e]) * pstride + e);
+          } else {
+            for (int c2 = 0; c2 < n_cta; ++c2) sv[e] += __ldcg(base + (int64_t)c2 * pstride + e);
+          }
+        }
+      }
+      float* dst = grad + (int64_t)l * D.layer_stride + o;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (live[e]) dst[e] = sv[e];
+    } else if (live[0] | live[1] | live[2] | live[3]) {
       const float4* src = reinterpret_cast<const float4*>(partial + (int64_t)l * D.layer_stride + jo);
       const int64_t step4 = pstride >> 2;
       float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -796,10 +912,10 @@ __device__ __forceinline__ float bt_reduce_loss(const float* partial, int64_t ps
 
 // stand-alone reduction (used when the backward kernel has no spare SMs for in-kernel reducers)
 __global__ void bt_reduce_kernel(const FlowmcFlowDesc D, const float* __restrict__ partial, int64_t pstride, int n_cta,
-                                 float* __restrict__ grad, float* __restrict__ loss) {
+                                 float* __restrict__ grad, float* __restrict__ loss, int R, int fc) {
   for (int l = blockIdx.y; l < D.n_layers; l += gridDim.y)
     bt_reduce_layer(D, partial, pstride, n_cta, grad, l, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x,
-                    (int)(D.layer_stride >> 2));
+                    (int)(D.layer_stride >> 2), R, fc);
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *loss = bt_reduce_loss(partial, pstride, n_cta);
 }
 
@@ -838,10 +954,69 @@ static int launch_bt(const FlowmcFlowDesc& D, const BtProgram& PR, const BtArgs&
   kern<<<b.n_cta + (fused ? n_red : 0), 4 * PARTS * 32 + 64, bytes, stream>>>(D, PR, b);
   flowmc_count_launch();
   if (!fused) {
-    bt_reduce_kernel<<<dim3(32, D.n_layers), 256, 0, stream>>>(D, b.partial, b.pstride, b.n_cta, b.grad, b.loss);
+    bt_reduce_kernel<<<dim3(32, D.n_layers), 256, 0, stream>>>(D, b.partial, b.pstride, b.n_cta, b.grad, b.loss, 1, 1);
     flowmc_count_launch();
   }
   cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    flowmc_set_error(cudaGetErrorString(e));
+    return FLOWMC_ERR_CUDA;
+  }
+  return FLOWMC_OK;
+}
+
+// Feature split: clusters of R CTAs per tile (see the kernel); the accumulators are reduced by the stand-alone kernel.
+template <int KB>
+static int launch_bt_split(const FlowmcFlowDesc& D, const BtProgram& PR, const BtArgs& a, int R, cudaStream_t stream) {
+  auto kern = flow_backward_tc_kernel<KB, 2, true>;
+  const size_t bytes = 1024 + (size_t)BT_STAGES * TC_STAGE_BYTES + ((sizeof(BtSmem<2>) + 15) & ~15) +
+                       (size_t)128 * BT_TS * sizeof(float) + (size_t)TC_M * (D.n_features + 1) * sizeof(float);
+  static size_t configured = 0;
+  if (bytes > configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      flowmc_set_error("flow backward (tensor-core path, feature split): cannot configure the kernel");
+      return FLOWMC_ERR_CUDA;
+    }
+    configured = bytes;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(4 * 2 * 32 + 64);
+  cfg.dynamicSmemBytes = bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)R;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  static int max_clusters[9] = {0};
+  if (max_clusters[R] == 0) {
+    cfg.gridDim = dim3((unsigned)R);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = 148 / (R == 8 ? 12 : R);
+    }
+    if (n * R > BT_MAX_CTAS) n = BT_MAX_CTAS / R;
+    max_clusters[R] = n;
+    tc_split_note_max_clusters(R, n);
+  }
+  BtArgs b = a;
+  const int n_clusters = (int)(a.n_tiles < max_clusters[R] ? a.n_tiles : max_clusters[R]);
+  b.split_r = R;
+  b.n_cta = n_clusters * R;
+  b.done = nullptr;
+  cfg.gridDim = dim3((unsigned)b.n_cta);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, D, PR, b);
+  flowmc_count_launch();
+  if (e == cudaSuccess) {
+    bt_reduce_kernel<<<dim3(32, D.n_layers), 256, 0, stream>>>(D, b.partial, b.pstride, b.n_cta, b.grad, b.loss, R,
+                                                               PR.fc);
+    flowmc_count_launch();
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess) {
     flowmc_set_error(cudaGetErrorString(e));
     return FLOWMC_ERR_CUDA;
@@ -873,8 +1048,10 @@ int64_t flow_backward_tc_act_bytes(const FlowmcFlowDesc& D, int64_t n) {
 }
 
 int64_t flow_backward_tc_partial_bytes(const FlowmcFlowDesc& D, int64_t n) {
-  const int64_t tiles = (n + TC_M - 1) / TC_M;
-  return (tiles < BT_MAX_CTAS ? tiles : BT_MAX_CTAS) * ((int64_t)D.n_layers * D.layer_stride + 4) * 4 +
+  // one accumulator per CTA of the backward kernel: up to one per SM (with the feature split a handful of tiles
+  // still occupies most SMs)
+  (void)n;
+  return (int64_t)BT_MAX_CTAS * ((int64_t)D.n_layers * D.layer_stride + 4) * 4 +
          (int64_t)(D.n_layers + 4) * 4;  // + the per-layer hand-off counters
 }
 
@@ -886,13 +1063,23 @@ int flow_backward_tc(const FlowmcFlowDesc& D, const float* params, uint8_t* wimg
   const int items = PR.n_items[0] > PR.n_items[1] ? PR.n_items[0] : PR.n_items[1];
   const int64_t tiles = (n + TC_M - 1) / TC_M;
   const int64_t pstride = (int64_t)D.n_layers * D.layer_stride + 4;
-  int* done = reinterpret_cast<int*>(partial + (tiles < BT_MAX_CTAS ? tiles : BT_MAX_CTAS) * pstride);
+  int* done = reinterpret_cast<int*>(partial + (int64_t)BT_MAX_CTAS * pstride);
   bt_pack_kernel<<<dim3(items, D.n_layers, 8), 256, 0, stream>>>(D, PR, params, wimg, done);
   flowmc_count_launch();
   BtArgs a;
   a.params = params; a.wimg = wimg; a.act_img = act_img; a.save_x = save_x; a.save_theta = save_theta; a.logp = logp;
   a.n = n; a.inv_n = inv_n; a.grad = grad; a.loss = loss; a.timing = g_bt_timing;
-  a.partial = partial; a.pstride = pstride; a.n_tiles = tiles; a.done = done; a.n_cta = 0;
+  a.partial = partial; a.pstride = pstride; a.n_tiles = tiles; a.done = done; a.n_cta = 0; a.split_r = 1;
+  {
+    // few tiles (a data-parallel rank's slice of the batch): clusters of CTAs share a tile, as in the forward pass
+    const int R = tc_split_factor(D, tiles);
+    if (R > 1 && D.num_bins <= 8) {
+      switch (D.num_bins) {
+        case 4: return launch_bt_split<4>(D, PR, a, R, stream);
+        case 8: return launch_bt_split<8>(D, PR, a, R, stream);
+      }
+    }
+  }
   // epilogue threads per sample row: 2.  FLOWMC_BT_PARTS=4 selects 16 epilogue warps -- measured SLOWER on B200
   // (profiles/r02_prof_train_c4_parts4.txt: C4 backward 562 vs 512 us, C5 783 vs 749 us): with one feature per thread
   // the adjoint stage shrinks only from 7.4K to 6.2K cycles per unit (it is latency-bound: the spline parameters come
