@@ -125,6 +125,14 @@ def _load() -> C.CDLL:
         "flowmc_realnvp_loss_grad_workspace_bytes": (i64, [C.POINTER(RealNVPDesc), i64]),
         "flowmc_realnvp_loss_grad": (i32, [C.POINTER(RealNVPDesc), vp, vp, vp, i64, f32, vp, vp, vp, i64, vp]),
         "flowmc_nf_accept_scan": (i32, [vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp]),
+        "flowmc_peer_block_bytes": (i64, [i64]),
+        "flowmc_peer_block_offset": (i64, [i64, i32]),
+        "flowmc_ipc_alloc": (i32, [i64, C.POINTER(vp), C.c_char_p]),
+        "flowmc_ipc_open": (i32, [C.c_char_p, C.POINTER(vp)]),
+        "flowmc_ipc_close": (i32, [vp]),
+        "flowmc_ipc_free": (i32, [vp]),
+        "flowmc_dp_reduce_adamw": (i32, [i32, i32, C.POINTER(vp), i64, vp, vp, vp, i64, f64, f64, f64, f64, f64, f64,
+                                       C.c_uint32, vp, vp]),
         "flowmc_nf_global_steps_workspace_bytes": (i64, [i64, i32, i32]),
         "flowmc_nf_global_steps": (i32, [C.POINTER(FlowDesc), vp, i32, vp, u32p, vp, vp, vp, vp, i64, i64, i64, i32,
                                          i32, i64, i64, C.POINTER(GlobalParams), u32p, vp, vp]),

@@ -13,8 +13,72 @@ BASELINE.json's north_star asks for:
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
+
 import torch
 import torch.distributed as dist
+
+
+class _DevMem:
+    """Device memory that torch did not allocate, exposed through __cuda_array_interface__ (float32 vector)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class PeerGroup:
+    """The ranks' exchange blocks for ``flowmc_dp_reduce_adamw`` (csrc/peer_reduce.cu): one CUDA-IPC allocation per
+    rank, mapped into every peer over NVLink.  Collective constructor (handles travel through torch.distributed)."""
+
+    def __init__(self, rank: int, world: int, n_params: int, device, group=None):
+        from ._lib import check, lib
+        self.rank, self.world, self.n_params = int(rank), int(world), int(n_params)
+        nbytes = int(lib.flowmc_peer_block_bytes(self.n_params))
+        if nbytes <= 0:
+            raise ValueError("peer exchange needs n_params % 4 == 0")
+        mine = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        with torch.cuda.device(device):
+            check(lib.flowmc_ipc_alloc(nbytes, C.byref(mine), handle))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.blocks = (C.c_void_p * self.world)()
+            self._opened = []
+            for k in range(self.world):
+                if k == self.rank:
+                    self.blocks[k] = mine.value
+                else:
+                    p = C.c_void_p()
+                    check(lib.flowmc_ipc_open(handles[k], C.byref(p)))
+                    self.blocks[k] = p.value
+                    self._opened.append(p.value)
+        self._mine = mine.value
+        self.epoch = 0
+        off = int(lib.flowmc_peer_block_offset(self.n_params, 0))
+        # the backward pass writes this rank's gradient (+ loss at index n_params) straight into the exchange block
+        self._mem = _DevMem(self._mine + off, self.n_params + 4)
+        self.grad_loss = torch.as_tensor(self._mem, device=device)
+        self.loss_out = torch.zeros(1, dtype=torch.float32, device=device)
+        dist.barrier(group=group)      # every peer has opened every block before anyone launches on them
+
+    def step(self, params, mu, nu, count, optim, stream) -> torch.Tensor:
+        """All-reduce of the ranks' gradients + clip + AdamW in one kernel; returns the all-reduced loss (device)."""
+        from ._lib import check, lib
+        self.epoch += 1
+        check(lib.flowmc_dp_reduce_adamw(self.rank, self.world, self.blocks, self.n_params, params.data_ptr(),
+                                         mu.data_ptr(), nu.data_ptr(), int(count), optim.learning_rate, optim.b1,
+                                         optim.b2, optim.eps, optim.weight_decay, optim.max_norm, self.epoch,
+                                         self.loss_out.data_ptr(), stream))
+        return self.loss_out
+
+    def failed(self) -> bool:
+        """True if a barrier of the kernel gave up waiting for a peer (bounded spin)."""
+        from ._lib import lib
+        off = int(lib.flowmc_peer_block_offset(self.n_params, 4))
+        flag = torch.as_tensor(_DevMem(self._mine + off, 4), device=self.grad_loss.device)
+        return bool(flag.view(torch.int32)[3].item() != 0)
 
 
 class ChainShard:
@@ -95,11 +159,25 @@ class ChainShard:
                 out[order[starts[r]:starts[r + 1]]] = blocks[r, :counts[r]]
         return out
 
+    def peer_group(self, n_params: int, device):
+        """The NVLink exchange group for the fused data-parallel optimiser step, or None when it does not apply: it
+        needs one process per GPU of ONE box over NCCL (world <= 8); ``FLOWMC_DP_PEER=0`` keeps NCCL + flowmc_clip_adamw."""
+        if (self.world_size < 2 or self.world_size > 8 or os.environ.get("FLOWMC_DP_PEER", "1") == "0"
+                or dist.get_backend(self.group) != "nccl" or torch.cuda.device_count() < self.world_size
+                or n_params % 4 != 0):
+            return None
+        key = (int(n_params), str(device))
+        if not hasattr(self, "_peer_groups"):
+            self._peer_groups = {}
+        if key not in self._peer_groups:
+            self._peer_groups[key] = PeerGroup(self.rank, self.world_size, n_params, device, self.group)
+        return self._peer_groups[key]
+
     def attach(self, local_stepper, global_stepper, model_trainer, model):
         local_stepper.set_chain_shard(self.offset, self.n_chains_global)
         global_stepper.set_chain_shard(self.offset, self.n_chains_global)
         model_trainer.set_chain_shard(self.offset, self.n_chains_global, self.all_reduce, self)
-        model.dp = (self.rank, self.world_size, self.all_reduce, self.broadcast)
+        model.dp = (self.rank, self.world_size, self.all_reduce, self.broadcast, self)
 
     def gather_chains(self, x: torch.Tensor) -> torch.Tensor:
         """All ranks' slabs concatenated along the chain axis (for users who want the full buffer)."""

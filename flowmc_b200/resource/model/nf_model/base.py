@@ -37,8 +37,16 @@ class _TrainScratch:
     def __init__(self, model, n_rows: int, batch_rows: int):
         dev = model.params.device
         d = model.desc
-        self.grad = torch.empty(int(d.n_params), dtype=torch.float32, device=dev)
-        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        # flat gradient + the loss in ONE buffer: the data-parallel step all-reduces both with a single collective.
+        # With a peer group (ranks of one box over NVLink) the buffer IS this rank's exchange block and the collective
+        # happens inside the optimiser kernel (flowmc_dp_reduce_adamw); otherwise NCCL all-reduce + flowmc_clip_adamw.
+        self.peer = None
+        if model.dp is not None and len(model.dp) > 4 and model.dp[1] > 1:
+            self.peer = model.dp[4].peer_group(int(d.n_params), dev)
+        self.grad_loss = self.peer.grad_loss if self.peer is not None else \
+            torch.zeros(int(d.n_params) + 4, dtype=torch.float32, device=dev)
+        self.grad = self.grad_loss[:int(d.n_params)]
+        self.loss = self.grad_loss[int(d.n_params):int(d.n_params) + 1]
         self.ws = torch.empty(max(16, int(model._loss_grad_workspace_bytes(batch_rows))), dtype=torch.uint8,
                               device=dev)
         self.perm = torch.empty(max(1, n_rows), dtype=torch.int32, device=dev)
@@ -131,8 +139,7 @@ class NFModel(Resource):
             # averages the replicas' gradients -- the same update on every rank, bit for bit
             all_reduce = self.dp[2]
             self.loss_and_grad(x, idx, sc, n_global=n * self.dp[1])
-            all_reduce(sc.grad)
-            all_reduce(sc.loss)
+            all_reduce(sc.grad_loss)
         else:
             rank, world, all_reduce = self.dp[:3]
             per = -(-n // world)
@@ -141,8 +148,11 @@ class NFModel(Resource):
                 self.loss_and_grad(x[lo:hi], None, sc, n_global=n)
             else:
                 self.loss_and_grad(x, idx[lo:hi], sc, n_global=n)
-            all_reduce(sc.grad)
-            all_reduce(sc.loss)
+            if sc.peer is not None:
+                # reduce-scatter + all-gather over NVLink peer memory, global norm, clip and AdamW in ONE kernel
+                state.count += 1
+                return sc.peer.step(self.params, state.mu, state.nu, state.count, optim, _stream())
+            all_reduce(sc.grad_loss)      # gradient + loss, one collective
         self._apply_update(optim, state, sc)
         return sc.loss
 

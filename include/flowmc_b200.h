@@ -280,6 +280,26 @@ FLOWMC_API int flowmc_nf_accept_scan(const uint32_t* chain_keys, int64_t n_chain
                                      const float* lp_prop, const float* lp_nf_prop, float* pos_buf, float* lp_buf,
                                      float* acc_buf, int64_t n_total, int64_t cursor, float* last_pos, void* stream);
 
+/* ---- data-parallel optimiser step over NVLink peer memory (csrc/peer_reduce.cu) ------------------------------
+ * One kernel = all-reduce of the ranks' gradients (reduce-scatter through peer loads, all-gather through peer stores,
+ * sums in rank order) + clip_by_global_norm + AdamW on the full vector, replacing NCCL all-reduce + flowmc_clip_adamw
+ * in NFModel.train_step when the ranks of one box train data-parallel.  Every rank owns one exchange block
+ * (flowmc_peer_block_bytes; layout through flowmc_peer_block_offset: 0 = grad [n_params + 4, loss at index n_params],
+ * 1 = reduced gradient, 2 = slice norms, 3 = flags, 4 = local counters) allocated with flowmc_ipc_alloc and opened
+ * by every peer with flowmc_ipc_open (CUDA IPC; the 64-byte handles travel over torch.distributed).  blocks[k] =
+ * rank k's block as mapped into THIS process (own block: the local pointer).  epoch = 1, 2, 3, ...: the same on every
+ * rank, one per call.  Every rank must make the call (it spins on its peers' flags). */
+FLOWMC_API int64_t flowmc_peer_block_bytes(int64_t n_params);
+FLOWMC_API int64_t flowmc_peer_block_offset(int64_t n_params, int what);
+FLOWMC_API int flowmc_ipc_alloc(int64_t bytes, void** ptr, unsigned char handle[64]);
+FLOWMC_API int flowmc_ipc_open(const unsigned char handle[64], void** ptr);
+FLOWMC_API int flowmc_ipc_close(void* ptr);
+FLOWMC_API int flowmc_ipc_free(void* ptr);
+FLOWMC_API int flowmc_dp_reduce_adamw(int rank, int world, void* const* blocks, int64_t n_params, float* params,
+                                      float* mu, float* nu, int64_t count, double lr, double b1, double b2, double eps,
+                                      double weight_decay, double max_norm, uint32_t epoch, float* loss_out,
+                                      void* stream);
+
 /* ---- training-set plumbing (strategy/train_model.py:66-81, nf_model/base.py:141-144,187-188) --------------- */
 /* jax.random.permutation(key, n) -> out device int32[n] */
 FLOWMC_API int64_t flowmc_random_permutation_workspace_bytes(int64_t n);

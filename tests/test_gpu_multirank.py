@@ -68,6 +68,26 @@ def _worker(rank, world, port, ret):
         assert torch.equal(mu[0], mu[1])
         out["dp_param_err"] = err / scale
 
+        # ---- 1b. the same training with the collective INSIDE the optimiser kernel (NVLink peer memory, CUDA IPC):
+        #          flowmc_dp_reduce_adamw instead of NCCL all-reduce + flowmc_clip_adamw.  Needs one GPU per rank.
+        if nccl:
+            m3 = MaskedCouplingRQSpline(d, 3, [32, 32], 8, frandom.PRNGKey(1), device=dev)
+            m3.dp = (shard.rank, shard.world_size, shard.all_reduce, shard.broadcast, shard)
+            o3 = Optimizer(m3, 2e-3)
+            _, best3, st3, loss3 = m3.train(frandom.PRNGKey(2), data, o3.optim, o3.optim_state, 2, bs, verbose=False)
+            pg = shard.peer_group(int(m3.desc.n_params), dev)
+            assert pg is not None and pg.epoch == 2 * (n_rows // bs) and not pg.failed(), "peer path not taken"
+            err3 = float((best1.params - best3.params).abs().max())
+            assert err3 <= DP_PARAM_RTOL * scale, f"peer-memory DP params differ by {err3:.3e} (scale {scale:.3g})"
+            assert float((loss1 - loss3).abs().max()) <= 1e-5 * max(1.0, float(loss1.abs().max()))
+            both = shard.all_gather_blocks(best3.params)
+            assert torch.equal(both[0], both[1]), "peer-memory replicas drifted apart"
+            for t3 in (st3.mu, st3.nu):
+                tt = shard.all_gather_blocks(t3)
+                assert torch.equal(tt[0], tt[1])
+            assert st3.count == st1.count
+            out["peer_param_err"] = err3 / scale
+
         # ---- 2. full bundle, chains sharded: buffers == rows of the single-process run until training, and the
         #         all-gathered training set == the single-process selection ------------------------------------
         n_chains, dd = 64, 5
