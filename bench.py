@@ -345,23 +345,25 @@ def local_plan(kernel, logpdf, n, d, n_steps, dev) -> dict:
     return dict(zip(names, [int(v) for v in out]))
 
 
-def flow_train_dp(dev, rank, world, iters=20, warm=5):
+def flow_train_dp(dev, rank, world, iters=20, warm=5, d=32, n_layers=10, tag="C4"):
     """C4 (BASELINE.json configs[3]): one NFModel.train_step on a GLOBAL batch of 16384 rows, data-parallel over the
-    `world` ranks (each rank takes 16384 / world rows; flat gradient + loss all-reduced over NCCL; identical fused
-    clip/AdamW on every rank).  Collective: every rank calls it.  Device time, max over ranks."""
+    `world` ranks: each rank takes 16384 / world rows (feature-split tensor-core kernels when that leaves it only a
+    few tiles), then gradient all-reduce + global-norm clip + AdamW in ONE kernel over NVLink peer memory
+    (flowmc_dp_reduce_adamw; FLOWMC_DP_PEER=0: NCCL all-reduce + flowmc_clip_adamw).  Collective: every rank calls it.
+    Device time, max over ranks."""
     import torch
     import torch.distributed as dist
     from flowmc_b200 import random as frandom
     from flowmc_b200.parallel import ChainShard
     from flowmc_b200.resource.model.nf_model.rqSpline import MaskedCouplingRQSpline
     from flowmc_b200.resource.optimizer import Optimizer
-    m = MaskedCouplingRQSpline(32, 10, [128, 128], 8, frandom.PRNGKey(1), device=dev)
+    m = MaskedCouplingRQSpline(d, n_layers, [128, 128], 8, frandom.PRNGKey(1), device=dev)
     if world > 1:
         sh = ChainShard(world, rank, world)
-        m.dp = (rank, world, sh.all_reduce, sh.broadcast)
+        m.dp = (rank, world, sh.all_reduce, sh.broadcast, sh)
     opt = Optimizer(m, 1e-3)
     bs = 16384
-    x = frandom.normal(frandom.PRNGKey(2), (bs * 4, 32), device=dev)
+    x = frandom.normal(frandom.PRNGKey(2), (bs * 4, d), device=dev)
     idx = torch.arange(bs, dtype=torch.int32, device=dev)
     from flowmc_b200.resource.model.nf_model.base import _TrainScratch
     sc = _TrainScratch(m, 0, bs)
@@ -381,10 +383,14 @@ def flow_train_dp(dev, rank, world, iters=20, warm=5):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    return {"workload": "C4: flow 32-D, 10 layers, [128,128], 8 bins; train_step on a global batch of 16384 rows "
-                        f"split over {world} GPU(s)", "n_gpus": world, "ms_per_step": ms,
+    collective = "none (single GPU)"
+    if world > 1:
+        collective = ("fused: reduce-scatter + all-gather over NVLink peer memory inside the optimiser kernel "
+                      "(flowmc_dp_reduce_adamw)") if sc.peer is not None else "NCCL all-reduce + flowmc_clip_adamw"
+    return {"workload": f"{tag}: flow {d}-D, {n_layers} layers, [128,128], 8 bins; train_step on a global batch of "
+                        f"16384 rows split over {world} GPU(s)", "n_gpus": world, "ms_per_step": ms,
             "samples_per_s": bs / ms * 1e3, "grad_allreduce_bytes": int(m.params.numel()) * 4 if world > 1 else 0,
-            "timing": f"{iters} back-to-back steps, CUDA events, max over ranks"}
+            "collective": collective, "timing": f"{iters} back-to-back steps, CUDA events, max over ranks"}
 
 
 def run_reference(args):

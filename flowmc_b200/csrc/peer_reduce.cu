@@ -31,7 +31,8 @@ namespace flowmc {
 namespace peer {
 
 constexpr int kMaxWorld = 8;
-constexpr int kCtas = 64;       // all co-resident (one wave): the kernel spins on flags
+constexpr int kMaxCtas = 1024;  // all CTAs must be co-resident (one wave): the kernel spins on flags; the launcher
+                                // takes min(4 per SM, what the occupancy query allows)
 constexpr int kThreads = 256;
 
 struct Block {  // byte offsets inside a rank's exchange block
@@ -44,8 +45,8 @@ __host__ __device__ inline Block block_layout(int64_t n) {
   b.gsum = pad256((n + 4) * 4);
   b.sumsq = b.gsum + pad256(n * 4);
   b.flags = b.sumsq + 256;          // [3 barriers][kMaxWorld] uint32
-  b.local = b.flags + 256;          // [0..2] grid-sync counters, [3] error flag, [4 .. 4 + kCtas) float partials
-  b.total = b.local + 1024;
+  b.local = b.flags + 256;          // [0..2] grid-sync counters, [3] error flag, [4 .. 4 + kMaxCtas) float partials
+  b.total = b.local + 256 + kMaxCtas * 4;
   return b;
 }
 
@@ -124,13 +125,21 @@ __global__ void __launch_bounds__(kThreads) dp_reduce_adamw_kernel(const Args a)
   const int64_t lo = min(n4, (int64_t)a.rank * per), hi = min(n4, lo + per);
   float ss = 0.0f;
   for (int64_t i = lo + gtid; i < hi; i += gstride) {
-    float4 s = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    for (int k = 0; k < a.world; ++k) {  // rank order: the sum is the same whoever computes it
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(a.base[k] + L.grad) + i);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
+    // all peers' loads in flight together (an NVLink round trip is ~2 us), summed in rank order: the sum is the same
+    // whoever computes it
+    float4 v[kMaxWorld];
+#pragma unroll
+    for (int k = 0; k < kMaxWorld; ++k)
+      v[k] = (k < a.world) ? __ldcg(reinterpret_cast<const float4*>(a.base[k] + L.grad) + i)
+                           : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 s = v[0];
+#pragma unroll
+    for (int k = 1; k < kMaxWorld; ++k)
+      if (k < a.world) { s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w; }
     ss = fmaf(s.x, s.x, ss); ss = fmaf(s.y, s.y, ss); ss = fmaf(s.z, s.z, ss); ss = fmaf(s.w, s.w, ss);
-    for (int k = 0; k < a.world; ++k) reinterpret_cast<float4*>(a.base[k] + L.gsum)[i] = s;
+#pragma unroll
+    for (int k = 0; k < kMaxWorld; ++k)
+      if (k < a.world) reinterpret_cast<float4*>(a.base[k] + L.gsum)[i] = s;
   }
   // squared norm of the slice: fixed-order two-stage sum (deterministic)
 #pragma unroll
@@ -150,11 +159,14 @@ __global__ void __launch_bounds__(kThreads) dp_reduce_adamw_kernel(const Args a)
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(local + 2, 1u) == a.epoch * gridDim.x - 1u) ? 1u : 0u;
     __syncthreads();
-    if (s_last && tid == 0) {
+    if (s_last && tid < 32) {  // fixed order: lane l takes partials l, l + 32, ...; then a fixed shuffle tree
       __threadfence();
       float s = 0.0f;
-      for (unsigned c = 0; c < gridDim.x; ++c) s += __ldcg(partials + c);
-      for (int k = 0; k < a.world; ++k) reinterpret_cast<float*>(a.base[k] + L.sumsq)[a.rank] = s;
+      for (unsigned c = tid; c < gridDim.x; c += 32) s += __ldcg(partials + c);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (tid == 0)
+        for (int k = 0; k < a.world; ++k) reinterpret_cast<float*>(a.base[k] + L.sumsq)[a.rank] = s;
     }
   }
   barrier(a, L, 1);  // every slice of gsum and every slice norm has landed everywhere
@@ -164,17 +176,27 @@ __global__ void __launch_bounds__(kThreads) dp_reduce_adamw_kernel(const Args a)
   for (int k = 0; k < a.world; ++k) tot += __ldcg(sumsq_mine + k);
   const float gn = sqrtf(tot);
   const bool keep = gn < a.max_norm;
-  for (int64_t i = gtid; i < n; i += gstride) {
-    float gi = __ldcg(gsum_mine + i);
-    if (!keep) gi = (gi / gn) * a.max_norm;
-    const float m = a.omb1 * gi + a.b1 * a.mu[i];
-    const float v = a.omb2 * (gi * gi) + a.b2 * a.nu[i];
-    a.mu[i] = m;
-    a.nu[i] = v;
-    float u = (m / a.bc1) / (sqrtf(v / a.bc2) + a.eps);
-    const float pi = a.params[i];
-    u = u + a.wd * pi;
-    a.params[i] = pi + (-a.lr) * u;
+  for (int64_t i = gtid; i < n4; i += gstride) {  // four elements per thread and iteration, 16-byte accesses
+    const float4 g4 = __ldcg(reinterpret_cast<const float4*>(gsum_mine) + i);
+    float4 m4 = reinterpret_cast<float4*>(a.mu)[i], v4 = reinterpret_cast<float4*>(a.nu)[i];
+    float4 p4 = reinterpret_cast<float4*>(a.params)[i];
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float gi = gg[e];
+      if (!keep) gi = (gi / gn) * a.max_norm;
+      const float m = a.omb1 * gi + a.b1 * mm[e];
+      const float v = a.omb2 * (gi * gi) + a.b2 * vv[e];
+      mm[e] = m;
+      vv[e] = v;
+      float u = (m / a.bc1) / (sqrtf(v / a.bc2) + a.eps);
+      u = u + a.wd * pp[e];
+      pp[e] = pp[e] + (-a.lr) * u;
+    }
+    reinterpret_cast<float4*>(a.mu)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(a.nu)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    reinterpret_cast<float4*>(a.params)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
   }
   if (a.loss_out != nullptr && gtid == 0) *a.loss_out = loss_sum;
   // No third barrier: gsum / sumsq of this rank are rewritten only in phase 2 of the NEXT call, i.e. after that call's
@@ -273,7 +295,20 @@ int flowmc_dp_reduce_adamw(int rank, int world, void* const* blocks, int64_t n_p
   a.omb2 = (float)(1.0 - b2);
   a.bc1 = 1.0f - powf(a.b1, (float)count);
   a.bc2 = 1.0f - powf(a.b2, (float)count);
-  dp_reduce_adamw_kernel<<<kCtas, kThreads, 0, (cudaStream_t)stream_>>>(a);
+  // one co-resident wave: 4 CTAs per SM if the occupancy allows it (the kernel has no shared memory to speak of)
+  static int grid = 0;
+  if (grid == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dp_reduce_adamw_kernel, kThreads, 0);
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    grid = sms * per_sm;
+    if (grid > kMaxCtas) grid = kMaxCtas;
+    if (grid < 1) grid = 64;
+  }
+  dp_reduce_adamw_kernel<<<grid, kThreads, 0, (cudaStream_t)stream_>>>(a);
   flowmc_count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
