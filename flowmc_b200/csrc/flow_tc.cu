@@ -170,7 +170,6 @@ struct TcArgs {
                       // tile's 128 rows) for the tensor-core weight-gradient GEMMs (flow_tc.cuh: tc_act_*)
   long long* timing;  // optional diagnostics: [3][256] clock64 stamps of CTA 0 (producer, MMA issuer, epilogue thread 0)
   int dump_vec;       // training forward: activation images leave with st.global.v4 (1) or bulk stores (0)
-  int train_ring4;    // training forward: four weight-ring slots, staging buffers in extra shared memory (if it fits)
   int dbg_skip;       // TIMING EXPERIMENTS ONLY (FLOWMC_TC_DBG_SKIP): 1 = no activation-image dump, 2 = no theta dump,
                       // 4 = no layer-input save -- the results are then useless to the backward pass
 };
@@ -215,9 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
   // commit -> producer -> L2 round trip, ~3.5K cycles; 4 slots give one chunk per round trip.)
   // Training gives the last 32 KB of the ring region to the activation-image staging buffers (4 KB per epilogue
   // warp): the weight stream is rate-bound, not depth-bound (a 5th slot changed nothing), 3 slots keep it fed.
-  // (a.train_ring4: the launcher found room for the staging buffers BEHIND the other shared-memory regions, so the
-  // training forward keeps all four ring slots too)
-  const int NST = (PAIR ? 2 : 1) * ((MODE == TC_TRAIN && !a.train_ring4) ? TC_STAGES - 1 : TC_STAGES);
+  constexpr int NST = (PAIR ? 2 : 1) * (MODE == TC_TRAIN ? TC_STAGES - 1 : TC_STAGES);
   constexpr int SLOT = PAIR ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES;
   TcSmem* S = reinterpret_cast<TcSmem*>(smem + TC_STAGES * TC_STAGE_BYTES);
   const int d = D.n_features;
@@ -231,8 +228,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
   float* xstage = sbias_all + ((D.n_layers * bias_stride + 3) & ~3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* astage_all = stages + (size_t)(TC_STAGES - 1) * TC_STAGE_BYTES;  // training only, see NST
-  if (MODE == TC_TRAIN && a.train_ring4)  // staging buffers behind the exchange buffer (which only SPLIT launches have)
-    astage_all = reinterpret_cast<uint8_t*>(xstage + (SPLIT ? ((d + 1) / 2) * TC_M : 0));
   const float* P = a.params;
   const int L = D.n_layers, nh = D.n_linear - 1;
   const int n_pass = (MODE == TC_NF) ? 2 : 1;
@@ -874,15 +869,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
   }
 }
 
-// FLOWMC_TC_RING4=0 keeps the training forward on the 3-slot ring with the staging buffers in the 4th slot
-static bool tc_train_ring4() {
-  static const bool on = [] {
-    const char* e = std::getenv("FLOWMC_TC_RING4");
-    return e == nullptr || e[0] != '0';
-  }();
-  return on;
-}
-
 template <int KB, int MODE, bool PAIR>
 static int launch_tc_impl(const FlowmcFlowDesc& D, const TcProgram& PR, const TcArgs& a, cudaStream_t stream) {
   auto kern = flow_tc_kernel<KB, MODE, PAIR>;
@@ -891,10 +877,6 @@ static int launch_tc_impl(const FlowmcFlowDesc& D, const TcProgram& PR, const Tc
                  (size_t)D.n_layers * ((D.n_linear - 1) * 128 + ((D.n_features + 1) / 2) * (3 * D.num_bins + 1)) *
                      sizeof(float);
   TcArgs b = a;
-  if (MODE == TC_TRAIN && !PAIR && tc_train_ring4() && bytes + TC_STAGE_BYTES <= 227 * 1024) {
-    b.train_ring4 = 1;  // room for the dump staging buffers behind everything else: the weight ring keeps 4 slots
-    bytes += TC_STAGE_BYTES;
-  }
   static size_t configured = 0;
   if (bytes > configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
@@ -995,12 +977,7 @@ int tc_split_factor(const FlowmcFlowDesc& D, int64_t tiles) {
 template <int KB>
 static int launch_tc_split(const FlowmcFlowDesc& D, const TcProgram& PR, const TcArgs& a, int R, cudaStream_t stream) {
   auto kern = flow_tc_kernel<KB, TC_TRAIN, false, true>;
-  size_t bytes = tc_split_smem_bytes(D);
-  TcArgs b = a;
-  if (tc_train_ring4() && bytes + TC_STAGE_BYTES <= 227 * 1024) {
-    b.train_ring4 = 1;
-    bytes += TC_STAGE_BYTES;
-  }
+  const size_t bytes = tc_split_smem_bytes(D);
   static size_t configured = 0;
   if (bytes > configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
@@ -1035,7 +1012,7 @@ static int launch_tc_split(const FlowmcFlowDesc& D, const TcProgram& PR, const T
   }
   const unsigned n_clusters = tiles < (unsigned)max_clusters[R] ? tiles : (unsigned)max_clusters[R];
   cfg.gridDim = dim3(n_clusters * (unsigned)R);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, D, PR, b);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, D, PR, a);
   flowmc_count_launch();
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) {
