@@ -50,11 +50,13 @@ struct TcItem {
   int lin;       // hidden: index of the Linear; chunk: first transformed-feature ordinal
   int n_feat;    // chunk: features in it
   uint32_t off;  // byte offset of the item's first stage from the layer's image base
-  int pad_;
+  uint32_t act_off;  // hidden: byte offset of the item's OUTPUT inside a (tile, layer) block of the activation image
 };
 struct TcProgram {
   int n_items[2];  // by layer parity (which features are transformed alternates, rqSpline.py:434)
   uint32_t layer_bytes[2];
+  uint32_t act_layer_bytes;  // tc_act_layer_bytes(D)
+  uint32_t pad_;
   TcItem items[2][TC_MAX_ITEMS];
 };
 
@@ -81,7 +83,7 @@ static int tc_build_program(const FlowmcFlowDesc& D, TcProgram* P) {
     for (int i = 0; i < nh; ++i) {
       TcItem& it = P->items[p][n++];
       it.kind = 0; it.K = D.dims[i]; it.n_kc = (it.K + 31) / 32; it.npad = D.dims[i + 1]; it.lin = i; it.n_feat = 0;
-      it.off = off; it.pad_ = 0;
+      it.off = off; it.act_off = (uint32_t)tc_act_item_off(D, i + 1);
       off += (uint32_t)it.n_kc * 2u * it.npad * 128u;
     }
     const int ntf = (d - p + 1) / 2;
@@ -91,12 +93,14 @@ static int tc_build_program(const FlowmcFlowDesc& D, TcProgram* P) {
       it.kind = 1; it.K = D.dims[nh]; it.n_kc = (it.K + 31) / 32; it.lin = c0;
       it.n_feat = (ntf - c0 < fc) ? ntf - c0 : fc;
       it.npad = (it.n_feat * NP + 15) & ~15;
-      it.off = off; it.pad_ = 0;
+      it.off = off; it.act_off = 0;
       off += (uint32_t)it.n_kc * 2u * it.npad * 128u;
     }
     P->n_items[p] = n;
     P->layer_bytes[p] = off;
   }
+  P->act_layer_bytes = (uint32_t)tc_act_layer_bytes(D);
+  P->pad_ = 0;
   return FLOWMC_OK;
 }
 
@@ -431,6 +435,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     // one lane sends the hi and the lo block with two bulk stores (asynchronous, full lines, off the LSU store
     // path, which the scattered 4-byte stores of a direct dump saturate).
     uint8_t* astage = astage_all + warp * 4096;
+    const uint32_t dump_sw = (uint32_t)(((lane >> 2) << 4) | ((lane & 3) << 2));  // see dump_rows
     // a.dump_vec (FLOWMC_TC_DUMP=vec, the default): the staged block leaves with coalesced 16-byte st.global from
     // all 32 lanes instead -- the bulk stores queue behind the weight stream in the SM's TMA unit, and waiting for
     // the previous one to release the buffer (bulk_wait_read) was what tripled the tanh epilogues of the training
@@ -440,22 +445,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
       if (a.dbg_skip & 1) return;
       if (!a.dump_vec && lane == 0) tc::bulk_wait_read<0>();  // the previous rows have left the buffer
       __syncwarp();
-      uint32_t* st = reinterpret_cast<uint32_t*>(astage);
+      // tc::packed_b_offset(u, lane) = (u >> 3) * 1024 + (u & 7) * 128 + (dump_sw ^ ((u & 7) << 4)): the lane part is
+      // hoisted (dump_sw), what is left per element is one XOR with a constant and an immediate offset
 #pragma unroll
       for (int u = 0; u < NB; ++u) {
-        const int o = tc::packed_b_offset(u, lane) >> 2;
-        st[o] = hi[u];
-        st[NB * 32 + o] = lo[u];
+        uint8_t* o = astage + ((u >> 3) * 1024 + (u & 7) * 128) + (dump_sw ^ (uint32_t)((u & 7) << 4));
+        *reinterpret_cast<uint32_t*>(o) = hi[u];
+        *reinterpret_cast<uint32_t*>(o + NB * 128) = lo[u];
       }
       if (a.dump_vec) {
         __syncwarp();
-        const float4* s4 = reinterpret_cast<const float4*>(astage);
-        float4* ghi = reinterpret_cast<float4*>(gimg + (size_t)n0 * 128);
-        float4* glo = reinterpret_cast<float4*>(gimg + (size_t)(n_rows + n0) * 128);
+        const float4* s4 = reinterpret_cast<const float4*>(astage) + lane;
+        float4* ghi = reinterpret_cast<float4*>(gimg + (size_t)n0 * 128) + lane;
+        float4* glo = ghi + (size_t)n_rows * 8;
 #pragma unroll
         for (int v = 0; v < NB / 4; ++v) {  // NB * 128 bytes per block = NB * 8 float4 = NB / 4 per lane
-          __stcs(ghi + v * 32 + lane, s4[v * 32 + lane]);
-          __stcs(glo + v * 32 + lane, s4[NB * 8 + v * 32 + lane]);
+          __stcs(ghi + v * 32, s4[v * 32]);
+          __stcs(glo + v * 32, s4[NB * 8 + v * 32]);
         }
         return;
       }
@@ -538,6 +544,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     row0 = tile * TC_M;
     grow = row0 + row;
     r = min(grow, a.n - 1);
+    // training: this tile's block of the activation image (NULL: no image wanted / idle tile)
+    uint8_t* const act_tile = (MODE == TC_TRAIN && a.act_img != nullptr && row0 < a.n)
+                                  ? a.act_img + (size_t)tile * L * PR.act_layer_bytes : nullptr;
     // ---- load / generate the tile ------------------------------------------------------------
     if (MODE == TC_NF) {
       const int64_t c = r / a.n_steps;
@@ -625,10 +634,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
             }
             tc::tmem_st8(t_ahi + lane_base + g * 8, hi);
             tc::tmem_st8(t_alo + lane_base + g * 8, lo);
-            if (MODE == TC_TRAIN && a.act_img != nullptr && row0 < a.n && (!SPLIT || (uint32_t)g % R == crank)) {
+            if (MODE == TC_TRAIN && act_tile != nullptr && (!SPLIT || (uint32_t)g % R == crank)) {
               const int npx = tc_pad16(d);
               dump_rows(std::integral_constant<int, 8>{}, hi, lo, g * 8,
-                        a.act_img + (tile * L + l) * tc_act_layer_bytes(D) + (size_t)q * 2 * npx * 128, npx);
+                        act_tile + (size_t)l * PR.act_layer_bytes + (size_t)q * 2 * npx * 128, npx);
             }
           }
           if (hf == 0 && crank == 0) ldacc += inv ? -(float)d * scale : (float)d * scale;
@@ -679,25 +688,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
-                  const float hv = tanh_ex2(v[u] + bias[c + u]);
-                  tc::split_tf32(hv, hi[u], lo[u]);
-                  if (MODE == TC_TRAIN && a.save_h != nullptr && grow < a.n)
-                    a.save_h[((int64_t)(l * nh + it.lin) * 128 + c + u) * a.n + grow] = hv;
-                }
-                if (MODE == TC_TRAIN && a.act_img != nullptr && row0 < a.n &&
-                    (!SPLIT || (uint32_t)(c >> 4) % R == crank)) {  // split: the redundant copies share the dump
-                  uint8_t* gimg = a.act_img + (tile * L + l) * tc_act_layer_bytes(D) +
-                                  tc_act_item_off(D, it.lin + 1) + (size_t)q * 2 * N * 128;
-                  dump_rows(std::integral_constant<int, 16>{}, hi, lo, c, gimg, N);
+                  v[u] = tanh_ex2(v[u] + bias[c + u]);
+                  tc::split_tf32(v[u], hi[u], lo[u]);
                 }
                 tc::tmem_st8(t_ahi + lane_base + c, hi);
                 tc::tmem_st8(t_ahi + lane_base + c + 8, hi + 8);
                 tc::tmem_st8(t_alo + lane_base + c, lo);
                 tc::tmem_st8(t_alo + lane_base + c + 8, lo + 8);
                 tc::tmem_wait_st();
+                tc::tc_fence_before();
+                arrive_mma(&S->a_ready[j]);  // the next GEMM starts on this K-chunk; the dumps below run under it
+                if (MODE == TC_TRAIN) {
+                  if (a.save_h != nullptr && grow < a.n) {  // (CUDA-core backward only)
+                    float* sh = a.save_h + ((int64_t)(l * nh + it.lin) * 128 + c) * a.n + grow;
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) sh[(int64_t)u * a.n] = v[u];
+                  }
+                  if (act_tile != nullptr && (!SPLIT || (uint32_t)(c >> 4) % R == crank))  // split: the redundant
+                    dump_rows(std::integral_constant<int, 16>{}, hi, lo, c,                  // copies share the dump
+                              act_tile + (size_t)l * PR.act_layer_bytes + it.act_off + (size_t)q * 2 * N * 128, N);
+                }
+              } else {
+                tc::tc_fence_before();
+                arrive_mma(&S->a_ready[j]);
               }
-              tc::tc_fence_before();
-              arrive_mma(&S->a_ready[j]);
             }
             arrive_mma(&S->acc_empty[slot]);
           } else {

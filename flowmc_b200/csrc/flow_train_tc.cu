@@ -49,12 +49,13 @@ struct BtItem {
   int n_feat;   // chunk: features
   int act;      // B from the activation image (1) or the transposed-weight image (0)
   uint32_t off; // byte offset inside the layer's weight image / the (tile, layer) activation image
+  uint32_t aoff; // BK_DGH: byte offset of the unit's own activations h_lin inside the (tile, layer) activation image
 };
 struct BtProgram {
   int n_items[2];
   uint32_t layer_bytes[2];
   int fc;
-  int pad_;
+  uint32_t act_layer_bytes;  // tc_act_layer_bytes(D)
   BtItem items[2][BT_MAX_ITEMS];
 };
 
@@ -63,7 +64,7 @@ static int bt_build_program(const FlowmcFlowDesc& D, BtProgram* P) {
   int fc = (128 / NP) & ~1;
   if (fc > 4) fc = 4;  // one 32-column slot of the A region per feature
   P->fc = fc;
-  P->pad_ = 0;
+  P->act_layer_bytes = (uint32_t)tc_act_layer_bytes(D);
   const int H = D.dims[nh];
   for (int p = 0; p < 2; ++p) {
     int n = 0;
@@ -74,21 +75,24 @@ static int bt_build_program(const FlowmcFlowDesc& D, BtProgram* P) {
       const int nf = (ntf - c0 < fc) ? ntf - c0 : fc;
       BtItem& dg = P->items[p][n++];
       dg.kind = BK_DG3; dg.N = H; dg.n_kc = nf; dg.K = nf * 32; dg.lin = c0; dg.n_feat = nf; dg.act = 0; dg.off = off;
+      dg.aoff = 0;
       off += (uint32_t)dg.n_kc * 2u * dg.N * 128u;
       BtItem& wg = P->items[p][n++];
       wg.kind = BK_WG3; wg.N = H; wg.n_kc = 4; wg.K = 128; wg.lin = c0; wg.n_feat = nf; wg.act = 1;
       wg.off = (uint32_t)tc_act_item_off(D, nh);  // h_last
+      wg.aoff = 0;
     }
     for (int i = nh - 1; i >= 0; --i) {
       if (n + 2 > BT_MAX_ITEMS) return FLOWMC_ERR_UNSUPPORTED;
       const int Nin = (i == 0) ? tc_pad16(d) : D.dims[i];
       BtItem& dg = P->items[p][n++];
       dg.kind = BK_DGH; dg.N = Nin; dg.K = D.dims[i + 1]; dg.n_kc = (dg.K + 31) / 32; dg.lin = i; dg.n_feat = 0;
-      dg.act = 0; dg.off = off;
+      dg.act = 0; dg.off = off; dg.aoff = (uint32_t)tc_act_item_off(D, i + 1);
       off += (uint32_t)dg.n_kc * 2u * dg.N * 128u;
       BtItem& wg = P->items[p][n++];
       wg.kind = BK_WGH; wg.N = Nin; wg.n_kc = 4; wg.K = 128; wg.lin = i; wg.n_feat = 0; wg.act = 1;
       wg.off = (uint32_t)tc_act_item_off(D, i);  // i == 0: x * mask, else h_{i-1}
+      wg.aoff = 0;
     }
     P->n_items[p] = n;
     P->layer_bytes[p] = off;
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
     for (int l = L - 1; l >= 0; --l) {
       const int p = l & 1;
       const uint8_t* wbase = a.wimg + bt_layer_base(PR, l);
-      const uint8_t* abase = a.act_img + (tile * L + l) * tc_act_layer_bytes(D);
+      const uint8_t* abase = a.act_img + (tile * L + l) * (size_t)PR.act_layer_bytes;
       for (int ii = 0; ii < PR.n_items[p]; ++ii) {
         const BtItem it = PR.items[p][ii];
         if (skip_item(it, ii)) continue;
@@ -359,11 +363,12 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
       tc::mbar_wait_cluster(&S->xbar[k], x_ph[k]);
       x_ph[k] ^= 1;
     };
+    const uint32_t img_sw = (uint32_t)(((lane >> 2) << 4) | ((lane & 3) << 2));  // lane part of an image byte offset
     // 8 consecutive A columns of this thread's row, from registers
     auto write_a8 = [&](int col, const float* v) {
       uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) tc::split_tf32(v[u], hi[u], lo[u]);
+      for (int u = 0; u < 8; ++u) tc::split_tf32_trunc(v[u], hi[u], lo[u]);
       tc::tmem_st8(t_ahi + lane_base + col, hi);
       tc::tmem_st8(t_alo + lane_base + col, lo);
     };
@@ -449,21 +454,26 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
       } else {
         // da = dh (1 - h^2): dh from acc 0, h from the forward pass's activation image (hi + lo)
         const int i = it.lin, N = D.dims[i + 1];
-        const uint8_t* abase = a.act_img + (tile * L + l) * tc_act_layer_bytes(D);
+        const uint8_t* abase = a.act_img + (tile * L + l) * (size_t)PR.act_layer_bytes;
         const uint32_t* himg =
-            reinterpret_cast<const uint32_t*>(abase + tc_act_item_off(D, i + 1) + (size_t)q * 2 * N * 128);
+            reinterpret_cast<const uint32_t*>(abase + it.aoff + (size_t)q * 2 * N * 128);
         int c_lo, c_hi;
         part(N / 16, c_lo, c_hi);
         const int c0 = c_lo * 16, cn = (c_hi - c_lo) * 16;  // this thread's columns [c0, c0 + cn), cn <= 64
         // 16 columns at a time; the activation words of the next group are requested before this group's are
         // consumed (the image comes from L2 / HBM: ~1 us away)
         uint32_t hb[2][32];
+        // word offset of (image row c0 + g4 * 16 + u, this lane) = tc::packed_b_offset(row, lane) / 4: c0 is a multiple
+        // of 16, so the row's 8-row group is (c0 >> 3) + 2 g4 + (u >> 3) and its swizzle phase u & 7 -- the lane part
+        // (img_sw) is hoisted, one XOR with a constant is left per element
+        const uint32_t* hrow = himg + (c0 >> 3) * 256;
         auto request = [&](int g4, uint32_t* dst) {
+          const uint32_t* h0 = hrow + g4 * 512;
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
-            const int o = tc::packed_b_offset(c0 + g4 * 16 + u, lane) >> 2;
-            dst[u] = __ldg(himg + o);
-            dst[16 + u] = __ldg(himg + N * 32 + o);
+            const uint32_t o = (uint32_t)((u >> 3) * 256 + (u & 7) * 32) + ((img_sw ^ (uint32_t)((u & 7) << 4)) >> 2);
+            dst[u] = __ldg(h0 + o);
+            dst[16 + u] = __ldg(h0 + N * 32 + o);
           }
         };
         if (cn > 0) request(0, hb[0]);
@@ -514,10 +524,9 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
       part(it.n_feat, i_lo, i_hi);
       for (int fi = i_lo; fi < i_hi; ++fi) {
         const float* th = a.save_theta + ((int64_t)nl * ((d + 1) / 2) + it.lin + fi) * NP * n + r;
-        if (lane == 0) {  // one request per 128-byte line (the warp's 32 rows)
-#pragma unroll
-          for (int u = 0; u < NP; ++u) asm volatile("prefetch.global.L2 [%0];" ::"l"(th + (int64_t)u * n));
-        }
+        // one request per 128-byte line (parameter u of the warp's 32 rows): lane u asks for line u
+        const float* th0 = th - lane;  // the warp's first row (clamped rows at the end of the batch: still in bounds)
+        if (lane < NP && grow - lane < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(th0 + (int64_t)lane * n));
       }
     };
     // dW tile of a finished unit (acc 1; lane = output unit m = t, columns = input units) -> this CTA's private
@@ -714,7 +723,7 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             bsum += v[u];
-            tc::split_tf32(v[u], hi[u], lo[u]);
+            tc::split_tf32_trunc(v[u], hi[u], lo[u]);
           }
           tc::tmem_st8(t_ahi + lane_base + hf * CPT + c, hi);
           tc::tmem_st8(t_alo + lane_base + hf * CPT + c, lo);

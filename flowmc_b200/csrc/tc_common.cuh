@@ -234,6 +234,15 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   lo = to_tf32_rn(x - __uint_as_float(hi));
 }
 
+// Two-instruction split for operands whose products only feed GRADIENTS (backward kernel): hi = x truncated to tf32
+// (one LOP), lo = x - hi left as a plain fp32 (one FADD) -- kind::tf32 ignores the 13 low mantissa bits of its
+// operands, so the tensor core truncates lo itself.  |x - hi - trunc(lo)| <= 2^-20 |x| (against 2^-22 with the two
+// roundings above): far inside the gradient tolerance, and 40 % of the rounding version's instructions.
+__device__ __forceinline__ void split_tf32_trunc(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
 // ---- UMMA descriptors --------------------------------------------------------------------------
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, dense 8-row groups (SBO = 1024 B), sm_100 version bit
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
