@@ -141,7 +141,7 @@ __global__ void tc_pack_flow_kernel(const FlowmcFlowDesc D, const TcProgram P, c
       }
     }
     uint32_t hi, lo;
-    tc::split_tf32(w, hi, lo);
+    tc::split_tf32_rn(w, hi, lo);
     float* stage = dst + (int64_t)kc * 2 * per_stage;
     const int o = tc::packed_b_offset(n, kk) >> 2;
     stage[o] = __uint_as_float(hi);
@@ -582,6 +582,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
     }
     // the tile (all rows, complete after an epi_bar) -> save_x[slot]: rows are contiguous in global memory, so the
     // CTA writes them as one coalesced stream
+    const int st_q = TC_EPI / d, st_r = TC_EPI - st_q * d;  // TC_EPI = st_q * d + st_r
     auto save_tile = [&](int slot) {
       if (a.dbg_skip & 4) return;
       const int64_t rows = min((int64_t)TC_M, a.n - row0);
@@ -589,9 +590,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
       // feature split: every CTA holds the whole tile; rank r writes its share of the rows
       const int e_lo = SPLIT ? (int)(crank * (TC_M / R)) * d : 0;
       const int e_hi = SPLIT ? min((int)rows, (int)((crank + 1) * (TC_M / R))) * d : (int)rows * d;
-      for (int e = e_lo + tid; e < e_hi; e += TC_EPI) {
-        const int rr = e / d;
-        dst[e] = xs[rr * xs_stride + (e - rr * d)];
+      // flat (coalesced) index e = rr * d + cc, advanced by TC_EPI per step without a division
+      int e = e_lo + tid;
+      int rr = e / d, cc = e - rr * d;
+      for (; e < e_hi; e += TC_EPI) {
+        dst[e] = xs[rr * xs_stride + cc];
+        rr += st_q;
+        cc += st_r;
+        if (cc >= d) {
+          cc -= d;
+          ++rr;
+        }
       }
     };
     float ldacc = 0.0f;
@@ -735,9 +744,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
 #pragma unroll
               for (int u = 0; u < NP && u < 32; ++u) raw[u] = v[u] + bl[i * NP + u];
               if (MODE == TC_TRAIN && a.save_theta != nullptr && grow < a.n && !(a.dbg_skip & 2)) {
-                float* dst = a.save_theta + ((int64_t)l * ((d + 1) / 2) + it.lin + i) * NP * a.n + grow;
+                // feature block [NP][n]: warp-uniform 64-bit base + 32-bit element offsets (tc path: n < 2^25 rows)
+                float* dst = a.save_theta + ((int64_t)l * ((d + 1) / 2) + it.lin + i) * NP * a.n;
+                const uint32_t o0 = (uint32_t)grow, nn = (uint32_t)a.n;
 #pragma unroll
-                for (int u = 0; u < NP; ++u) dst[(int64_t)u * a.n] = raw[u];
+                for (int u = 0; u < NP; ++u) dst[o0 + (uint32_t)u * nn] = raw[u];
               }
             };
             int i = i_lo;

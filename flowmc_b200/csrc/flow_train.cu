@@ -585,7 +585,9 @@ int flowmc_flow_loss_grad(const FlowmcFlowDesc* D, const float* params, const fl
   float* logp = layer_inputs + pad4i((int64_t)(D->n_layers + 1) * n * D->n_features);
   float* save_h = logp + pad4i(n);
   float* save_theta = save_h + pad4i((int64_t)D->n_layers * (D->n_linear - 1) * 128 * n);
-  const bool tcf = flow_tc_enabled(*D);
+  // (the training kernels address a feature's [NP][n] block of spline parameters with 32-bit element offsets: batches
+  // beyond 2^26 rows take the CUDA-core path)
+  const bool tcf = flow_tc_enabled(*D) && n <= ((int64_t)1 << 26);
   // The tensor-core forward can also hand its hidden activations and spline parameters to the backward kernel
   // (no conditioner recompute: -27 % instructions).  Measured on B200 (profiles/r01_flow_backward_c4_ncu.txt) the
   // CUDA-core backward is bound by the L2 latency of its weight loads, not by instruction count, and the extra

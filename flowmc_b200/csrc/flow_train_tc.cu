@@ -132,7 +132,7 @@ __global__ void bt_pack_kernel(const FlowmcFlowDesc D, const BtProgram P, const 
       if (k < D.dims[it.lin + 1] && n < D.dims[it.lin]) w = PL[D.off_W[it.lin] + (int64_t)k * D.dims[it.lin] + n];
     }
     uint32_t hi, lo;
-    tc::split_tf32(w, hi, lo);
+    tc::split_tf32_rn(w, hi, lo);
     float* stage = dst + (int64_t)kc * 2 * per_stage;
     const int o = tc::packed_b_offset(n, kk) >> 2;
     stage[o] = __uint_as_float(hi);
@@ -429,9 +429,11 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
           if (fi < it.n_feat) {
             const int fo = it.lin + fi, f = p + 2 * fo;
             float raw[NP], dr[32], gx;
-            const float* th = a.save_theta + ((int64_t)l * ((d + 1) / 2) + fo) * NP * n + r;
+            // feature block [NP][n]: warp-uniform 64-bit base + 32-bit element offsets (n < 2^25 rows, checked by the host)
+            const float* th = a.save_theta + ((int64_t)l * ((d + 1) / 2) + fo) * NP * n;
+            const uint32_t o0 = (uint32_t)r, nn = (uint32_t)n;
 #pragma unroll
-            for (int u = 0; u < NP; ++u) raw[u] = th[(int64_t)u * n];
+            for (int u = 0; u < NP; ++u) raw[u] = th[o0 + (uint32_t)u * nn];
             const float xa = (xin[f] + shift) * e;
             rq_backward<KB, true>(raw, D.range_min, D.range_max, xa, gr[f], gld, gx, dr);
             gr[f] = gx;
@@ -567,9 +569,20 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
           tc::tmem_wait_ld();
           if (active) {
             if (permuted) {
+              // column group k (4 columns) of this row: blk + k * rows * 4; 32-bit element offsets from one base
+              float* pb = blk + (int64_t)(c0 >> 2) * rows * 4;
+              const uint32_t gs4 = (uint32_t)rows * 4u;
+              const int ng = min(8, (ncols - c0 + 3) >> 2);
+              if (first) {
 #pragma unroll
-              for (int u = 0; u < 32; u += 4)
-                if (c0 + u < ncols) store4(blk + (int64_t)((c0 + u) >> 2) * rows * 4, v + u);
+                for (int k = 0; k < 8; ++k)
+                  if (k < ng)
+                    *reinterpret_cast<float4*>(pb + (uint32_t)k * gs4) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                  if (k < ng) store4(pb + (uint32_t)k * gs4, v + 4 * k);
+              }
             } else {
               // first Linear with n_features not a multiple of 4: canonical layout, live (conditioning) columns only
               float* dst = GL + D.off_W[it.lin] + (int64_t)t * ldc;

@@ -229,7 +229,15 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 // clear the 13 low mantissa bits.  Two ALU-pipe instructions instead of one XU-pipe conversion -- the epilogues
 // are XU-bound (ex2 / rcp), so the split must not add to that pipe.  (Inf/NaN never occur in these operands.)
 __device__ __forceinline__ uint32_t to_tf32_rn(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+// (lo is left as the plain fp32 remainder: kind::tf32 ignores the 13 low mantissa bits of its operands, i.e. the
+// tensor core truncates it itself; |lo| <= 2^-11 |x|, so the truncation costs <= 2^-21 |x| -- the order of the
+// hi * lo term 3xTF32 drops anyway -- and saves two of the five instructions per element)
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32_rn(x);
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// both halves rounded to nearest (weight images: packed once per parameter update, not in an epilogue)
+__device__ __forceinline__ void split_tf32_rn(float x, uint32_t& hi, uint32_t& lo) {
   hi = to_tf32_rn(x);
   lo = to_tf32_rn(x - __uint_as_float(hi));
 }

@@ -22,7 +22,7 @@ __global__ void tc_pack_b_kernel(const float* __restrict__ W, int N, int K, int 
     const int k = kc * 32 + kk;
     const float w = (n < N && k < K) ? W[(int64_t)n * K + k] : 0.0f;
     uint32_t hi, lo;
-    tc::split_tf32(w, hi, lo);
+    tc::split_tf32_rn(w, hi, lo);
     float* stage = img + (int64_t)kc * 2 * Npad * 32;
     const int off = tc::packed_b_offset(n, kk) / 4;
     stage[off] = __uint_as_float(hi);
