@@ -156,6 +156,7 @@ struct BtArgs {
   int64_t n_tiles;
   long long* timing;  // optional diagnostics: clock64 stamps of epilogue thread 0 of CTA 0
   int split_r;        // feature split: CTAs per tile (cluster size), 1 = one CTA per tile
+  int dbg_skip;       // timing experiments only (FLOWMC_BT_DBG_SKIP): 1 = no dW stores, 2 = no dW tile reads either
   int n_cta;          // CTAs that process tiles; CTAs beyond them (if any) are REDUCERS, see bt_reduce_layer
   int* done;          // [L] tile CTAs that have finished layer l (reducer hand-off) + [1] reduction work counter;
                       // zeroed by bt_pack_kernel
@@ -564,10 +565,11 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
         const int c0 = hf * CPT + g2 * 32;
         if (c0 < npad) {
           float v[32];
+          if (a.dbg_skip & 2) continue;
           tc::tmem_ld16(tbase + 384 + lane_base + c0, v);
           if (c0 + 16 < npad) tc::tmem_ld16(tbase + 384 + lane_base + c0 + 16, v + 16);
           tc::tmem_wait_ld();
-          if (active) {
+          if (active && !(a.dbg_skip & 1)) {
             if (permuted) {
               // column group k (4 columns) of this row: blk + k * rows * 4; 32-bit element offsets from one base
               float* pb = blk + (int64_t)(c0 >> 2) * rows * 4;
@@ -799,7 +801,7 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
       if (c >= Lr * per_layer) break;
       const int l = Lr - 1 - c / per_layer, ch = c % per_layer;
       bt_reduce_layer(D, a.partial, a.pstride, a.n_cta, a.grad, l, ch * gpc + (int)threadIdx.x, (int)blockDim.x,
-                      min(n_groups, (ch + 1) * gpc));
+                      min(n_groups, (ch + 1) * gpc), SPLIT ? a.split_r : 1, SPLIT ? PR.fc : 1);
       if (c == Lr * per_layer - 1 && threadIdx.x == 0) *a.loss = bt_reduce_loss(a.partial, a.pstride, a.n_cta);
     }
   }
@@ -1029,11 +1031,15 @@ static int launch_bt_split(const FlowmcFlowDesc& D, const BtProgram& PR, const B
   const int n_clusters = (int)(a.n_tiles < max_clusters[R] ? a.n_tiles : max_clusters[R]);
   b.split_r = R;
   b.n_cta = n_clusters * R;
-  b.done = nullptr;
-  cfg.gridDim = dim3((unsigned)b.n_cta);
+  // clusters the tiles leave free become in-kernel reducers, like the spare CTAs of the one-CTA-per-tile launch (all
+  // clusters of the grid are co-resident: the reducers' spin-wait cannot starve a tile cluster)
+  const int n_red = (max_clusters[R] - n_clusters) * R;
+  const bool fused = n_red >= 8 && a.done != nullptr;
+  if (!fused) b.done = nullptr;
+  cfg.gridDim = dim3((unsigned)(b.n_cta + (fused ? n_red : 0)));
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, D, PR, b);
   flowmc_count_launch();
-  if (e == cudaSuccess) {
+  if (e == cudaSuccess && !fused) {
     bt_reduce_kernel<<<dim3(32, D.n_layers), 256, 0, stream>>>(D, b.partial, b.pstride, b.n_cta, b.grad, b.loss, R,
                                                                PR.fc);
     flowmc_count_launch();
@@ -1092,6 +1098,11 @@ int flow_backward_tc(const FlowmcFlowDesc& D, const float* params, uint8_t* wimg
   a.params = params; a.wimg = wimg; a.act_img = act_img; a.save_x = save_x; a.save_theta = save_theta; a.logp = logp;
   a.n = n; a.inv_n = inv_n; a.grad = grad; a.loss = loss; a.timing = g_bt_timing;
   a.partial = partial; a.pstride = pstride; a.n_tiles = tiles; a.done = done; a.n_cta = 0; a.split_r = 1;
+  static const int dbg_skip = [] {
+    const char* e = std::getenv("FLOWMC_BT_DBG_SKIP");
+    return e != nullptr ? std::atoi(e) : 0;
+  }();
+  a.dbg_skip = dbg_skip;
   {
     // few tiles (a data-parallel rank's slice of the batch): clusters of CTAs share a tile, as in the forward pass
     const int R = tc_split_factor(D, tiles);
