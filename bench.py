@@ -255,6 +255,8 @@ def flow_extras(dev):
     st = timed_calls(lambda: m.train_step(x, opt.optim, opt.optim_state, idx), 8, 3)
     ms = st["median"]
     out["flow_train_c4"] = {"samples_per_s": bs / ms * 1e3, "batch": bs, "ms_per_step": st,
+                            "tensor_pipe_active_ncu": {k: nc[k] for k in ("flow_tc_train_forward_c4", "flow_backward_tc_c4")
+                                                       if k in nc},
                             "useful_tflops": 3 * fl * bs / ms / 1e9,
                             "useful_frac_of_measured_tf32_burst": (3 * fl * bs / ms / 1e9 / tf32_burst) if tf32_burst else None,
                             "note": "training forward (tcgen05, leaves spline parameters + packed activation images) + "
