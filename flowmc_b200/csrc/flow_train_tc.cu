@@ -1114,11 +1114,9 @@ int flow_backward_tc(const FlowmcFlowDesc& D, const float* params, uint8_t* wimg
     }
   }
   // epilogue threads per sample row: 2.  FLOWMC_BT_PARTS=4 selects 16 epilogue warps -- measured SLOWER on B200
-  // (profiles/r02_prof_train_c4_parts4.txt: C4 backward 562 vs 512 us, C5 783 vs 749 us): with one feature per thread
-  // the adjoint stage shrinks only from 7.4K to 6.2K cycles per unit (it is latency-bound: the spline parameters come
-  // from L2, the MUFU chains are dependent) while the 96-register budget spills and the dW stores contend; the
-  // per-unit chain A-write -> dgrad MMAs -> transposed A-write -> wgrad MMAs through the ONE operand region of tensor
-  // memory is what bounds the kernel, not the epilogue's instruction count.  Kept for A/B runs.
+  // (profiles/r02_prof_train_c4_parts4.txt: C4 backward 562 vs 512 us, C5 783 vs 749 us): the epilogue is a
+  // latency-bound serial program (IPC 0.22 per warp) that more warps would help, but a 640-thread CTA
+  // leaves 96 registers per thread and the adjoint stage then spills 240 bytes per thread.  Kept for A/B runs.
   static const int parts = [] {
     const char* e = std::getenv("FLOWMC_BT_PARTS");
     return (e != nullptr && e[0] == '4') ? 4 : 2;
