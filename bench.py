@@ -369,8 +369,11 @@ def flow_train_dp(dev, rank, world, iters=20, warm=5, d=32, n_layers=10, tag="C4
     idx = torch.arange(bs, dtype=torch.int32, device=dev)
     from flowmc_b200.resource.model.nf_model.base import _TrainScratch
     sc = _TrainScratch(m, 0, bs)
+    # the call sequence NFModel.train_epoch runs per batch (train_step with its per-step lookups bound once)
+    step = m._bind_train_step(x, opt.optim, opt.optim_state, sc, bs)
+    idx_ptr = idx.data_ptr()
     for _ in range(warm):
-        m.train_step(x, opt.optim, opt.optim_state, idx, sc)
+        step(idx_ptr)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -378,7 +381,7 @@ def flow_train_dp(dev, rank, world, iters=20, warm=5, d=32, n_layers=10, tag="C4
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        m.train_step(x, opt.optim, opt.optim_state, idx, sc)
+        step(idx_ptr)
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)

@@ -156,6 +156,46 @@ class NFModel(Resource):
         self._apply_update(optim, state, sc)
         return sc.loss
 
+    def _bind_train_step(self, x, optim, state, sc, n: int):
+        """``train_step`` on ``n`` rows ``idx`` of ``x`` with everything that does not change between steps resolved
+        once: returns ``f(idx_ptr) -> loss`` (device tensor; ``idx_ptr`` = device address of int32[n]).  Same calls,
+        same order, same results as ``train_step``; the caller holds the device context."""
+        x = x.contiguous()
+        stream = _stream()
+        x_ptr = x.data_ptr()
+        dp = self.dp if (self.dp is not None and self.dp[1] > 1) else None
+        lo, rows, n_glob = 0, n, n
+        if dp is not None:
+            if n < dp[1] * self.dp_min_rows_per_rank:
+                n_glob = n * dp[1]
+            else:
+                per = -(-n // dp[1])
+                lo = min(n, dp[0] * per)
+                rows = min(n, (dp[0] + 1) * per) - lo
+        inv = 1.0 / float(n_glob)
+        grad_ptr, loss_ptr = sc.grad.data_ptr(), sc.loss.data_ptr()
+        ws_ptr, ws_bytes = sc.ws.data_ptr(), sc.ws.numel()
+        prepare = getattr(self, "_prepare_bound", None)
+        prepare = prepare(stream) if prepare is not None else self.prepare
+        loss_grad, apply_update = self._loss_grad_call, self._apply_update
+        peer = sc.peer if dp is not None else None
+        all_reduce = dp[2] if dp is not None else None
+        keep = x                                       # the bound pointers stay valid while the closure lives
+
+        def step(idx_ptr: int):
+            prepare()
+            check(loss_grad(x_ptr, idx_ptr + 4 * lo, rows, inv, grad_ptr, loss_ptr, ws_ptr, ws_bytes, stream))
+            if peer is not None:
+                state.count += 1
+                return peer.step(self.params, state.mu, state.nu, state.count, optim, stream)
+            if all_reduce is not None:
+                all_reduce(sc.grad_loss)
+            apply_update(optim, state, sc)
+            return sc.loss
+
+        step.keep = keep
+        return step
+
     def train_epoch(self, rng, optim, state, data, batch_size, scratch=None):
         """base.py:127-151: permutation batches (incomplete tail skipped), in place; returns the last
         batch's loss (device tensor)."""
@@ -168,8 +208,14 @@ class NFModel(Resource):
             with torch.cuda.device(data.device):
                 check(lib.flowmc_random_permutation(key.ctypes.data_as(_u32p), n, sc.perm.data_ptr(),
                                                     sc.perm_ws.data_ptr(), sc.perm_ws.numel(), _stream()))
-            for b in range(steps):
-                value = self.train_step(data, optim, state, sc.perm[b * batch_size:(b + 1) * batch_size], sc)
+            # every step of the epoch runs the same call sequence on a different slice of the permutation: bind it
+            # once (pointers, stream, rank slice) -- the per-step host cost is what bounds a data-parallel rank whose
+            # GPU work per step is a few hundred microseconds
+            with torch.cuda.device(data.device):
+                step = self._bind_train_step(data, optim, state, sc, int(batch_size))
+                perm_ptr = sc.perm.data_ptr()
+                for b in range(steps):
+                    value = step(perm_ptr + 4 * b * int(batch_size))
         else:
             value = self.train_step(data, optim, state, None, sc)
         return value

@@ -152,6 +152,16 @@ class MaskedCouplingRQSpline(NFModel):
                                           _stream()))
         self.desc.tc_image, self.desc.tc_terms = self._tc_image.data_ptr(), int(self.tc_terms)
 
+    def _prepare_bound(self, stream):
+        """``prepare`` for a loop of training steps: the image exists and the shape cannot change, only the weights
+        do -- one pack call per step, everything else resolved here."""
+        self.prepare()
+        if not self.desc.tc_terms:
+            return lambda: None
+        desc, params_ptr, image_ptr = C.byref(self.desc), self.params.data_ptr(), self._tc_image.data_ptr()
+        pack = lib.flowmc_flow_tc_pack
+        return lambda: check(pack(desc, params_ptr, image_ptr, stream))
+
     # ---- bijection ---------------------------------------------------------------------------
     def _prep(self, x):
         x = torch.as_tensor(x, dtype=torch.float32)
