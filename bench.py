@@ -95,6 +95,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def wait_first_row(self, timeout_s: float):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.02)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -122,6 +127,89 @@ class ClockSampler:
                 "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class NvmlSampler:
+    """The same clocks / event reasons read in-process through NVML (the library nvidia-smi wraps) by a thread: no
+    process start-up and one cheap query per field instead of nvidia-smi's full device refresh per row."""
+
+    def __init__(self, index: int, period_s: float = 0.05):
+        self.index, self.period, self.rows, self.ok = index, period_s, [], False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    @staticmethod
+    def _physical_index(i: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[i])
+            except Exception:
+                return i
+        return i
+
+    def start(self):
+        if self.ok:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def _run(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), int(get_reasons(self.h))))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def wait_first_row(self, timeout_s: float):
+        t0 = time.perf_counter()
+        while self.ok and not self.rows and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.01)
+
+    def stop(self):
+        if not self.ok:
+            return None
+        self._stop.set()
+        self.thread.join(timeout=2)
+        nv = self.nv
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        reasons = sorted(nm for nm, b in bits.items() if any(r & b for _, r in self.rows))
+        sm = [float(c) for c, _ in self.rows]
+        busy = [c for c in sm if c > 0.5 * self.max_sm]
+        return {"sm_mhz": float(np.median(busy or sm)) if sm else None, "sm_max_mhz": float(self.max_sm),
+                "reasons": reasons, "samples": len(sm),
+                "source": "NVML in-process (the counters nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.* prints), "
+                          "every 50 ms during the timed region"}
+
+
+def make_clock_sampler(index: int):
+    """NVML in-process when pynvml is importable, else the nvidia-smi -lms loop.  FLOWMC_BENCH_CLOCKS=smi forces the
+    latter (measured: its queries stall kernel launches for up to 40 ms, which lands in a 50 ms timed region)."""
+    if os.environ.get("FLOWMC_BENCH_CLOCKS", "nvml") != "smi":
+        s = NvmlSampler(index)
+        if s.ok:
+            return s
+    return ClockSampler(index)
+
+
+def gate(ms: float = 8.0):
+    """Keeps the GPU busy for ~ms milliseconds (a spin kernel) so that the first timed launches are already queued when
+    the start event fires: without it the first interval of a back-to-back loop contains the host's latency to enqueue
+    the first call -- 0.6 to 2.4 ms here, 32 ms once -- while the GPU idles (measured: it was always step 1 that was
+    slow, profiles/r02_bench_first_step_artifact.txt)."""
+    import torch
+    torch.cuda._sleep(int(ms * 1.9e6))
+
+
 def stats(ms: list) -> dict:
     a = np.asarray(ms, dtype=np.float64)
     return {"min": float(a.min()), "median": float(np.median(a)), "mean": float(a.mean()), "max": float(a.max()),
@@ -136,6 +224,7 @@ def timed_calls(fn, iters: int, warm: int) -> dict:
         fn()
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    gate(3.0)
     ev[0].record()
     for i in range(iters):
         fn()
@@ -222,11 +311,9 @@ def flow_extras(dev):
 
     nc = ncu_constants()
     out = {}
-    try:
-        out["tf32_peak_measured"] = tf32_peak(dev)
-    except Exception as ex:
-        out["tf32_peak_measured"] = {"error": repr(ex)}
-    tf32_burst = out["tf32_peak_measured"].get("burst_tflops")
+    tf32_burst = None   # the TF32 GEMM probe runs LAST (two seconds at the power cap leave the clocks low for the
+                        # kernels that follow it: an earlier build measured the flow extras 1.5-1.8x slow that way);
+                        # the fractions of the measured peak are filled in at the end
     # C4 flow: 32-D, 10 layers, [128,128], 8 bins
     m = MaskedCouplingRQSpline(32, 10, [128, 128], 8, frandom.PRNGKey(1), device=dev)
     n = 148 * 128 * 4
@@ -283,6 +370,20 @@ def flow_extras(dev):
                                  "useful_tflops": 2 * useful_flops(d, 8, 128, 8) * n_chains * n_steps / ms / 1e9,
                                  "note": "65536 chains x 10 NFProposal steps: flow inverse + forward, target, accept scan"}
     return out
+
+
+def tf32_fractions(out: dict, dev):
+    """Runs the TF32 GEMM probe (after every other extra) and fills the fractions of the measured peak in."""
+    try:
+        out["tf32_peak_measured"] = tf32_peak(dev)
+    except Exception as ex:
+        out["tf32_peak_measured"] = {"error": repr(ex)}
+    tf32_burst = out["tf32_peak_measured"].get("burst_tflops")
+    if tf32_burst and "flow_log_prob_c4" in out and "flow_train_c4" in out:
+        lp, tr = out["flow_log_prob_c4"], out["flow_train_c4"]
+        lp["issued_frac_of_measured_tf32_burst"] = lp["issued_tflops"] / tf32_burst
+        lp["useful_frac_of_measured_tf32_burst"] = lp["useful_tflops"] / tf32_burst
+        tr["useful_frac_of_measured_tf32_burst"] = tr["useful_tflops"] / tf32_burst
 
 
 def local_extras(dev):
@@ -347,7 +448,7 @@ def local_plan(kernel, logpdf, n, d, n_steps, dev) -> dict:
     return dict(zip(names, [int(v) for v in out]))
 
 
-def flow_train_dp(dev, rank, world, iters=20, warm=5, d=32, n_layers=10, tag="C4"):
+def flow_train_dp(dev, rank, world, iters=20, warm=5, d=32, n_layers=10, tag="C4", bs=16384):
     """C4 (BASELINE.json configs[3]): one NFModel.train_step on a GLOBAL batch of 16384 rows, data-parallel over the
     `world` ranks: each rank takes 16384 / world rows (feature-split tensor-core kernels when that leaves it only a
     few tiles), then gradient all-reduce + global-norm clip + AdamW in ONE kernel over NVLink peer memory
@@ -364,8 +465,7 @@ def flow_train_dp(dev, rank, world, iters=20, warm=5, d=32, n_layers=10, tag="C4
         sh = ChainShard(world, rank, world)
         m.dp = (rank, world, sh.all_reduce, sh.broadcast, sh)
     opt = Optimizer(m, 1e-3)
-    bs = 16384
-    x = frandom.normal(frandom.PRNGKey(2), (bs * 4, d), device=dev)
+    x = frandom.normal(frandom.PRNGKey(2), (bs * 2, d), device=dev)
     idx = torch.arange(bs, dtype=torch.int32, device=dev)
     from flowmc_b200.resource.model.nf_model.base import _TrainScratch
     sc = _TrainScratch(m, 0, bs)
@@ -379,6 +479,7 @@ def flow_train_dp(dev, rank, world, iters=20, warm=5, d=32, n_layers=10, tag="C4
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gate(3.0)
     e0.record()
     for _ in range(iters):
         step(idx_ptr)
@@ -393,7 +494,7 @@ def flow_train_dp(dev, rank, world, iters=20, warm=5, d=32, n_layers=10, tag="C4
         collective = ("fused: reduce-scatter + all-gather over NVLink peer memory inside the optimiser kernel "
                       "(flowmc_dp_reduce_adamw)") if sc.peer is not None else "NCCL all-reduce + flowmc_clip_adamw"
     return {"workload": f"{tag}: flow {d}-D, {n_layers} layers, [128,128], 8 bins; train_step on a global batch of "
-                        f"16384 rows split over {world} GPU(s)", "n_gpus": world, "ms_per_step": ms,
+                        f"{bs} rows split over {world} GPU(s)", "n_gpus": world, "global_batch": bs, "ms_per_step": ms,
             "samples_per_s": bs / ms * 1e3, "grad_allreduce_bytes": int(m.params.numel()) * 4 if world > 1 else 0,
             "collective": collective, "timing": f"{iters} back-to-back steps, CUDA events, max over ranks"}
 
@@ -487,17 +588,22 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (`value`): K calls back to back ------------------------------------------
+    # the clock sampler (nvidia-smi -lms) is started BEFORE the warm-up and must have delivered its first row before
+    # the timed region begins: its start-up (NVML initialisation on an 8-GPU box takes up to a second) stalls launches
+    # for milliseconds and used to land inside the timed steps (per_step_ms.max 8.1 ms against a 4.88 ms median)
+    sampler = make_clock_sampler(local_rank)
+    if rank == 0:
+        sampler.start()
     k = key
     for _ in range(args.warmup):
         k, _ = step_device(k)
     barrier()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
+        sampler.wait_first_row(5.0)
     launches0 = lib.flowmc_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    gate()
     ev[0].record()
     for i in range(args.steps):
         k, last = step_device(k)
@@ -571,6 +677,9 @@ def run_ours(args):
         scaled = {}
         try:
             scaled["flow_train_c4_dp"] = flow_train_dp(dev, rank, world)
+            if world > 1:
+                # the same step with the per-GPU work held at 16384 rows (a user scaling batch_size with the GPUs)
+                scaled["flow_train_c4_dp_weak"] = flow_train_dp(dev, rank, world, bs=16384 * world)
         except Exception as ex:  # the headline line must still be printed
             scaled["flow_train_c4_dp"] = {"error": repr(ex)}
         try:
@@ -589,6 +698,7 @@ def run_ours(args):
         try:
             extras = flow_extras(dev)
             extras.update(local_extras(dev))
+            tf32_fractions(extras, dev)
         except Exception as ex:
             extras = {"error": repr(ex)}
     peak, peak_src = measured_peak()
@@ -617,6 +727,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "launch_plan": plan,
         "per_step_ms": {"back_to_back": kst, "sync_per_step": stats(sync_ms),
+                        "back_to_back_each": [round(v, 4) for v in kernel_ms],
                         "note": "CUDA-event time of each of the K timed steps (one TakeSerialSteps call = "
                                 f"{plan['n_launches']} launches of local_steps_kernel); `value` uses the back-to-back total"},
         "clocks": clocks,
