@@ -210,6 +210,33 @@ def gate(ms: float = 8.0):
     torch.cuda._sleep(int(ms * 1.9e6))
 
 
+def bind_near_gpu(index: int):
+    """Pins this process to the CPUs of the GPU's NUMA node (sysfs local_cpulist of its PCI function) so that the
+    pinned host buffers of the e2e leg are first-touched on the memory the GPU's root port is attached to -- with 8
+    ranks on one box the D2H copies otherwise all land on one socket.  Returns (original mask, description)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if not cpus or cpus == old:
+            return old, f"GPU {bdf}: local CPUs {txt or '?'} = the whole mask, not bound"
+        os.sched_setaffinity(0, cpus)
+        return old, f"GPU {bdf}: bound to its NUMA node's CPUs {txt}"
+    except Exception as ex:
+        return None, f"not bound ({type(ex).__name__}: {ex})"
+
+
 def stats(ms: list) -> dict:
     a = np.asarray(ms, dtype=np.float64)
     return {"min": float(a.min()), "median": float(np.median(a)), "mean": float(a.mean()), "max": float(a.max()),
@@ -573,6 +600,7 @@ def run_ours(args):
     # initial positions: normal(split(PRNGKey(0))[1], (n_global, d)) -- this rank's rows
     x0_all_key = frandom.split(frandom.PRNGKey(0))[1]
     x0 = frandom.normal(x0_all_key, (n_global, D), device=dev)[rank * n:(rank + 1) * n].contiguous()
+    old_mask, affinity_note = bind_near_gpu(local_rank)   # before the pinned buffers are first touched
     x0_host = x0.cpu().pin_memory()
     key = frandom.PRNGKey(1)
     plan = local_plan(resources["kernel"], resources["logpdf"], n, D, N_LOCAL_STEPS, dev)
@@ -665,6 +693,8 @@ def run_ours(args):
         res_e2e[full] = chain_steps_per_step * e2e_steps / float(dt.item())
     h2d = x0_host.numel() * 4
     d2h_full = (out_pos.numel() + out_lp.numel() + out_acc.numel() + out_last.numel()) * 4
+    if old_mask is not None:
+        os.sched_setaffinity(0, old_mask)   # the CPU legs below use every host core
     del out_pos, out_lp, out_acc
     del resources["positions"], resources["log_prob"], resources["acceptance"]
     torch.cuda.empty_cache()
@@ -716,7 +746,7 @@ def run_ours(args):
         "config": make_config(world),
         "acceptance_rate": acc_rate,
         "e2e": {"value": res_e2e[True], "unit": "chain-steps/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h_full,
+                "d2h_bytes_per_step": d2h_full, "host_affinity_rank0": affinity_note,
                 "note": "TakeSerialSteps call with pinned-host initial positions in and ALL sample buffers "
                         "(positions, log-probs, accept flags, last position) copied to pinned host memory"},
         "e2e_device_resident_buffers": {
