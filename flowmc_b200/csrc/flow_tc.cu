@@ -706,16 +706,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
                 tc::tmem_st8(t_alo + lane_base + c + 8, lo + 8);
                 tc::tmem_wait_st();
                 tc::tc_fence_before();
-                arrive_mma(&S->a_ready[j]);  // the next GEMM starts on this K-chunk; the dumps below run under it
-                if (MODE == TC_TRAIN) {
-                  if (a.save_h != nullptr && grow < a.n) {  // (CUDA-core backward only)
-                    float* sh = a.save_h + ((int64_t)(l * nh + it.lin) * 128 + c) * a.n + grow;
+                arrive_mma(&S->a_ready[j]);  // the next GEMM starts on this K-chunk
+                if (MODE == TC_TRAIN && a.save_h != nullptr && grow < a.n) {  // (CUDA-core backward only)
+                  float* sh = a.save_h + ((int64_t)(l * nh + it.lin) * 128 + c) * a.n + grow;
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) sh[(int64_t)u * a.n] = v[u];
-                  }
-                  if (act_tile != nullptr && (!SPLIT || (uint32_t)(c >> 4) % R == crank))  // split: the redundant
-                    dump_rows(std::integral_constant<int, 16>{}, hi, lo, c,                  // copies share the dump
-                              act_tile + (size_t)l * PR.act_layer_bytes + it.act_off + (size_t)q * 2 * N * 128, N);
+                  for (int u = 0; u < 16; ++u) sh[(int64_t)u * a.n] = v[u];
                 }
               } else {
                 tc::tc_fence_before();
@@ -723,6 +718,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) flow_tc_kernel(const FlowmcFlow
               }
             }
             arrive_mma(&S->acc_empty[slot]);
+            if (MODE == TC_TRAIN && act_tile != nullptr) {
+              // Activation image of this layer's output, AFTER every K-chunk has been handed over: the words are read
+              // back from the operand region (the next GEMM only reads it; this thread rewrites it no earlier than its
+              // next tanh epilogue / the next layer's affine, in program order), so the 128 KB of stores per tile run
+              // under the next GEMM's MMAs instead of in front of them.
+              uint8_t* gimg = act_tile + (size_t)l * PR.act_layer_bytes + it.act_off + (size_t)q * 2 * N * 128;
+              for (int j = 0; j < (N + 31) / 32; ++j) {
+                const int c = (2 * j + hf) * 16;
+                if (c < N && (!SPLIT || (uint32_t)(c >> 4) % R == crank)) {  // split: the redundant copies share the dump
+                  float fh[16], fl[16];
+                  tc::tmem_ld16(t_ahi + lane_base + c, fh);
+                  tc::tmem_ld16(t_alo + lane_base + c, fl);
+                  tc::tmem_wait_ld();
+                  uint32_t hi[16], lo[16];
+#pragma unroll
+                  for (int u = 0; u < 16; ++u) {
+                    hi[u] = __float_as_uint(fh[u]);
+                    lo[u] = __float_as_uint(fl[u]);
+                  }
+                  dump_rows(std::integral_constant<int, 16>{}, hi, lo, c, gimg, N);
+                }
+              }
+            }
           } else {
             // ---- spline epilogue: this thread's half of the chunk's features ------------------------
             const int nf = it.n_feat;
