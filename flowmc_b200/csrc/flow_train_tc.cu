@@ -164,7 +164,7 @@ struct BtArgs {
 
 #define BT_STAMP()                                                                                \
   do {                                                                                            \
-    if (a.timing != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 256) a.timing[n_stamp++] = clock64(); \
+    if (a.timing != nullptr && blockIdx.x == 0 && tid == 0 && n_stamp < 252) a.timing[n_stamp++] = clock64(); \
   } while (0)
 
 __device__ __forceinline__ void bt_reduce_layer(const FlowmcFlowDesc& D, const float* partial, int64_t pstride,
@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
     for (int i = 0; i < 2; ++i) tc::mbar_init(&S->xbar[i], R * EPI_WARPS);
     tc::fence_mbar_init();
   }
+  if (a.timing != nullptr && blockIdx.x == 0 && tid == 0) a.timing[252] = clock64();  // CTA 0 entered the kernel
   if (warp == EPI_WARPS) tc::tmem_alloc<512>(&S->tmem_base);
   tc::tc_fence_before();
   __syncthreads();
@@ -767,6 +768,7 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
   if (SPLIT) tc::cluster_sync();  // no CTA leaves while a peer may still read its shared memory / arrive on its barriers
   tc::tc_fence_after();
   if (warp == EPI_WARPS) tc::tmem_dealloc<512>(tbase);
+  if (a.timing != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.timing[253] = clock64();  // CTA 0: tiles done
   }  // tile CTA
   if (a.done == nullptr) return;  // reduction by bt_reduce_kernel
 
@@ -804,6 +806,7 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
                       min(n_groups, (ch + 1) * gpc), SPLIT ? a.split_r : 1, SPLIT ? PR.fc : 1);
       if (c == Lr * per_layer - 1 && threadIdx.x == 0) *a.loss = bt_reduce_loss(a.partial, a.pstride, a.n_cta);
     }
+    if (a.timing != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.timing[254] = clock64();  // CTA 0: reduction done
   }
 }
 

@@ -16,6 +16,12 @@ m.loss_and_grad(x)
 torch.cuda.synchronize()
 lib.flowmc_trace_tc_timeline(None)
 t = buf.cpu().numpy().reshape(4, 256)[3]
+if t[252] > 0 and t[253] > 0:
+    first = t[:252][t[:252] > 0]
+    print(f"CTA 0 (cycles): kernel entry -> first unit prepared {int(first[0] - t[252])}, first -> last stamp "
+          f"{int(first[-1] - first[0])}, last stamp -> tiles done {int(t[253] - first[-1])}, tiles done -> reduction done "
+          f"{int(t[254] - t[253]) if t[254] > 0 else -1}")
+t = t[:252]
 v = t[t > 0]
 v = v - v[0]
 print("backward epilogue stamps per chunk: [operand written, dgrad done, transposed written, wgrad done, reduced]")
