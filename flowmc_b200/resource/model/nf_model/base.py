@@ -254,6 +254,11 @@ class NFModel(Resource):
             with nvtx_range(f"flowmc/train_epoch[{epoch}]"):
                 value = model.train_epoch(input_rng, optim, state, data, batch_size, sc)
             loss_values[epoch] = float(value.item())              # the reference's per-epoch host read
+            if sc.peer is not None and sc.peer.failed():
+                # a cross-GPU barrier of flowmc_dp_reduce_adamw gave up waiting (bounded spin): the parameters of
+                # this epoch are not trustworthy -- fail loudly instead of sampling from them
+                raise RuntimeError("flowmc_b200: a peer rank did not reach the data-parallel optimiser step "
+                                   "(flowmc_dp_reduce_adamw barrier timeout)")
             if loss_values[epoch] < best_loss:
                 if best_model is self:
                     best_model = model.clone()
