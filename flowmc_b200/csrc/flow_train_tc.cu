@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
         // Exchange buffer X[j][row] = T (free here: the last unit's transposed reads are behind an epi_bar).  Every CTA
         // publishes, for its share of the columns: conditioning feature j -> ITS partial of the conditioner-input
         // gradient (acc 0); transformed feature j it owns -> the spline adjoint's dL/dx (already in gr[j]).
-        const int fc = PR.items[l & 1][0].n_feat;  // features per (full) chunk
+        const int fc = PR.fc;  // features per (full) chunk: 2 or 4
         for (int c = (j_lo / 16) * 16; c < j_hi; c += 16) {
           float v[16];
           tc::tmem_ld16(tbase + 256 + lane_base + c, v);
@@ -626,26 +626,73 @@ __global__ void __launch_bounds__(4 * PARTS * 32 + 64, 1) flow_backward_tc_kerne
             if (j >= j_lo && j < j_hi) T[j * BT_TS + t] = (((j + l) & 1) == 1) ? v[u] : gr[j];
           }
         }
+        BT_STAMP();        // (split) contributions written
         cluster_round(0);  // every CTA's contributions are in its T
-        for (int j = j_lo; j < j_hi; ++j) {
-          float ga;
-          if (((j + l) & 1) == 1) {  // conditioning: dL/dy_j + the sum of the CTAs' partials, in rank order
-            float tot = 0.0f;
-            for (uint32_t k = 0; k < R; ++k)
-              tot += (k == crank) ? T[j * BT_TS + t] : tc::ld_cluster_f32(t_remote[k] + 4u * (uint32_t)(j * BT_TS));
-            ga = gr[j] + tot;
-          } else {                   // transformed: the owner's dL/dx
-            const uint32_t own = (uint32_t)(((j - (l & 1)) >> 1) / fc) % R;
-            ga = (own == crank) ? gr[j] : tc::ld_cluster_f32(t_remote[own] + 4u * (uint32_t)(j * BT_TS));
+        BT_STAMP();        // (split) round 0 complete
+        // The peers' values come through distributed shared memory (~200 cycles a load): all loads of a block of JB
+        // columns are issued before the first one is consumed.  fc (2 or 4) and R (2, 4 or 8) are powers of two: the
+        // owner of transformed feature j is a shift and a mask -- the warp is latency-bound here and the two integer
+        // divisions per column of the first version were most of the loop (profiles/r02_bt_timeline_c5_split.txt:
+        // 38K -> 23K cycles per layer).
+        constexpr int JB = 4;
+        const int fc_shift = fc >= 4 ? 2 : 1;
+        const uint32_t rmask = R - 1u;
+        auto owner = [&](int j) -> uint32_t { return ((uint32_t)((j - (l & 1)) >> 1) >> fc_shift) & rmask; };
+        // One copy of the loop per cluster size, unrolled over exactly RR ranks (a generic copy unrolled over 8 ranks with
+        // `k < R` predicates was 150 instructions per column; the warp runs at IPC ~0.2 here).
+        auto gather = [&](auto rr_tag) {
+          constexpr uint32_t RR = decltype(rr_tag)::value;
+          uint32_t tr[RR];  // this thread's column of T in every CTA of the cluster
+#pragma unroll
+          for (uint32_t k = 0; k < RR; ++k) tr[k] = t_remote[k];
+          for (int j0 = j_lo; j0 < j_hi; j0 += JB) {
+            float pv[JB][RR];  // [column][rank]
+            float xv[JB];
+#pragma unroll
+            for (int u = 0; u < JB; ++u) {
+              const int j = j0 + u;
+              const bool cond = ((j + l) & 1) == 1;
+              const uint32_t own = owner(j);
+              xv[u] = j < j_hi ? xin[j] : 0.0f;
+#pragma unroll
+              for (uint32_t k = 0; k < RR; ++k) {
+                pv[u][k] = 0.0f;
+                if (j < j_hi && k != crank && (cond || k == own))
+                  pv[u][k] = tc::ld_cluster_f32(tr[k] + 4u * (uint32_t)(j * BT_TS));
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < JB; ++u) {
+              const int j = j0 + u;
+              if (j < j_hi) {
+                float ga = gr[j];
+                if (((j + l) & 1) == 1) {  // conditioning: dL/dy_j + the sum of the CTAs' partials, in rank order
+                  float tot = 0.0f;
+#pragma unroll
+                  for (uint32_t k = 0; k < RR; ++k) tot += (k == crank) ? T[j * BT_TS + t] : pv[u][k];
+                  ga += tot;
+                } else {                   // transformed: the owner's dL/dx (this CTA's own gr[j] if it is the owner)
+                  const uint32_t own = owner(j);
+#pragma unroll
+                  for (uint32_t k = 0; k < RR; ++k)
+                    if (k == own && k != crank) ga = pv[u][k];
+                }
+                const float xa = (xv[u] + shift) * e;
+                if (valid) {
+                  ssc += ga * xa;
+                  ssh += ga * e;
+                }
+                gr[j] = ga * e;
+              }
+            }
           }
-          const float xa = (xin[j] + shift) * e;
-          if (valid) {
-            ssc += ga * xa;
-            ssh += ga * e;
-          }
-          gr[j] = ga * e;
-        }
+        };
+        if (R == 2) gather(std::integral_constant<uint32_t, 2>{});
+        else if (R == 4) gather(std::integral_constant<uint32_t, 4>{});
+        else gather(std::integral_constant<uint32_t, 8>{});
+        BT_STAMP();        // (split) peers' values gathered
         cluster_round(1);  // every CTA has read what it needs: T may be rewritten by the next unit
+        BT_STAMP();        // (split) round 1 complete
       } else
       for (int c = (j_lo / 16) * 16; c < j_hi; c += 16) {
         float v[16];

@@ -8,7 +8,8 @@ from flowmc_b200.resource.model.nf_model.rqSpline import MaskedCouplingRQSpline
 
 d, L = (32, 10) if (len(sys.argv) < 2 or sys.argv[1] == "c4") else (64, 8)
 m = MaskedCouplingRQSpline(d, L, [128, 128], 8, frandom.PRNGKey(1))
-x = frandom.normal(frandom.PRNGKey(2), (16384, d))
+rows = int(sys.argv[2]) if len(sys.argv) > 2 else 16384   # few rows (e.g. 2048) -> the feature-split kernels
+x = frandom.normal(frandom.PRNGKey(2), (rows, d))
 m.loss_and_grad(x)
 buf = torch.zeros(4 * 256, dtype=torch.int64, device="cuda")
 lib.flowmc_trace_tc_timeline(buf.data_ptr())
