@@ -455,6 +455,18 @@ def local_extras(dev):
     out["mala_c5_local"] = {"chain_steps_per_s": rate, "ms_per_call": st, "acceptance_rate": acc, "launch_plan": plan,
                             "workload": "C5 local phase: 64-D 8-component mixture, 65536 chains, MALA 0.1, 50 steps per call",
                             "hbm_frac": rate * 4 * (64 + 2) / 1e9 / measured_peak()[0]}
+    # C2 with the SAME covariance as a dense precision matrix (reported separately; 2 d^2 flop per gradient)
+    try:
+        idx = np.arange(128)
+        cov = (0.9 ** np.abs(idx[:, None] - idx[None, :])).astype(np.float64)
+        rate, st, acc, plan = run(MALA(0.1), T.dense_gaussian(np.linalg.inv(cov).astype(np.float32)), 8192, 128, 200)
+        out["mala_c2_dense_precision"] = {
+            "chain_steps_per_s": rate, "ms_per_call": st, "acceptance_rate": acc, "launch_plan": plan,
+            "workload": "C2 variant: the AR(1) covariance as a dense 128 x 128 precision matrix (no structure used), 8192 "
+                        "chains, MALA 0.1, 200 steps per call",
+            "gradient_tflops": rate * 2.0 * 128 * 128 / 1e12, "hbm_frac": rate * 4 * (128 + 2) / 1e9 / measured_peak()[0]}
+    except Exception as ex:
+        out["mala_c2_dense_precision"] = {"error": repr(ex)}
     return out
 
 
@@ -728,6 +740,14 @@ def run_ours(args):
         try:
             extras = flow_extras(dev)
             extras.update(local_extras(dev))
+            try:   # C5 with the bundle's default flow (4 x [32, 32] x 8, RQSpline_MALA.py defaults), SURVEY 8d
+                from scripts.bench_sampler import run_sampler
+                r = run_sampler(dev, 0, 1, flow=(4, [32, 32]))
+                extras["sampler_c5_bundle_default_flow"] = {k: r[k] for k in (
+                    "workload", "wall_s", "phase_ms_rank0", "flow_train_ms_per_step", "sampler_chain_steps_per_s",
+                    "ess_per_s", "global_acceptance", "local_acceptance")}
+            except Exception as ex:
+                extras["sampler_c5_bundle_default_flow"] = {"error": repr(ex)}
             tf32_fractions(extras, dev)
         except Exception as ex:
             extras = {"error": repr(ex)}

@@ -48,7 +48,7 @@ class Timed:
         return out
 
 
-def run_sampler(dev, rank, world, n_chains=65536, d=64, quick=False):
+def run_sampler(dev, rank, world, n_chains=65536, d=64, quick=False, flow=(8, [128, 128])):
     """One full C5 run (strong scaling: ``n_chains`` in TOTAL, sharded over ``world`` ranks).  Collective: every rank
     must call it.  Returns the result dict (identical on every rank apart from rank-0 phase times)."""
     from flowmc_b200 import random as frandom, targets as T
@@ -57,7 +57,7 @@ def run_sampler(dev, rank, world, n_chains=65536, d=64, quick=False):
     from flowmc_b200.Sampler import Sampler
 
     cfg = dict(n_local_steps=50, n_global_steps=10, n_training_loops=4, n_production_loops=4, n_epochs=5,
-               mala_step_size=0.1, rq_spline_hidden_units=[128, 128], rq_spline_n_bins=8, rq_spline_n_layers=8,
+               mala_step_size=0.1, rq_spline_hidden_units=list(flow[1]), rq_spline_n_bins=8, rq_spline_n_layers=int(flow[0]),
                learning_rate=1e-3, batch_size=16384, n_max_examples=1048576)
     if quick:
         cfg.update(n_training_loops=2, n_production_loops=2, n_epochs=2, n_max_examples=131072)
@@ -123,7 +123,7 @@ def run_sampler(dev, rank, world, n_chains=65536, d=64, quick=False):
         ess = float(t.item())
     return {
         "workload": f"C5: full Sampler (MALA + NFProposal + TrainModel), {d}-D 8-component mixture, {n_chains} chains "
-                    f"in total over {world} GPU(s) (strong scaling), flow 8x[128,128]x8",
+                    f"in total over {world} GPU(s) (strong scaling), flow {flow[0]}x{list(flow[1])}x8",
         "config": cfg, "n_gpus": world, "wall_s": wall, "wall_s_host_rank0": wall_host, "phase_ms_rank0": ms,
         "timing": "CUDA events around Sampler.sample on each rank, max over ranks",
         "local_chain_steps_per_s": local_steps / (ms["local_stepper"] * 1e-3),
